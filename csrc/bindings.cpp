@@ -1,0 +1,229 @@
+// pybind11 / torch bindings for the tutel_b200 native runtime (`tutel_b200._C`).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <string>
+#include <vector>
+
+#include "cpu_kernels.h"
+#include "gemm_sm100.h"
+#include "jit_nvrtc.h"
+#include "moe_kernels.h"
+#include "p2p_kernels.h"
+#include "symm_heap.h"
+
+namespace {
+
+#define TB_CHECK_CUDA(expr)                                                                          \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    TORCH_CHECK(_e == cudaSuccess, "tutel_b200 CUDA error: ", cudaGetErrorString(_e), " at ", #expr); \
+  } while (0)
+
+int gemm_dtype_of(const at::Tensor& t) {
+  switch (t.scalar_type()) {
+    case at::kBFloat16: return tb::DT_BF16;
+    case at::kHalf: return tb::DT_FP16;
+    case at::kFloat: return tb::DT_FP32;
+    case at::kFloat8_e4m3fn: return tb::DT_E4M3;
+    case at::kFloat8_e5m2: return tb::DT_E5M2;
+    default: TORCH_CHECK(false, "unsupported dtype for tutel_b200 GEMM: ", t.scalar_type());
+  }
+}
+
+int elem_type_of(const at::Tensor& t) {
+  switch (t.scalar_type()) {
+    case at::kFloat: return tb::ET_F32;
+    case at::kHalf: return tb::ET_F16;
+    case at::kBFloat16: return tb::ET_BF16;
+    default: TORCH_CHECK(false, "unsupported dtype for tutel_b200 dispatch kernels: ", t.scalar_type());
+  }
+}
+
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+// a: [G, M, K] (a_mn=false) or [G, K, M] (a_mn=true); b: [Gb, N, K] (b_mn=false) or [Gb, K, N] (b_mn=true);
+// d: [G, M, N].  Innermost dims contiguous.  Pointer-table / flag arguments are raw device addresses (0 = off).
+void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, bool a_mn, bool b_mn, int64_t epilogue,
+          const c10::optional<at::Tensor>& bias, const c10::optional<at::Tensor>& aux,
+          const c10::optional<at::Tensor>& row_counts, double alpha, int64_t b_group_div, int64_t cta_group,
+          int64_t block_n, int64_t d_ptr_table, int64_t signal_ptr_table, int64_t wait_flags,
+          int64_t wait_rows_per_flag, int64_t wait_flags_per_group, int64_t wait_target, int64_t max_ctas) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && d.is_cuda(), "tutel_b200.gemm: CUDA tensors required");
+  TORCH_CHECK(a.dim() == 3 && b.dim() == 3 && d.dim() == 3, "tutel_b200.gemm: expected 3-D operands");
+  TORCH_CHECK(a.stride(2) == 1 && b.stride(2) == 1 && d.stride(2) == 1, "tutel_b200.gemm: innermost dim must be contiguous");
+  TORCH_CHECK(a.scalar_type() == b.scalar_type(), "tutel_b200.gemm: A/B dtype mismatch");
+  const c10::cuda::CUDAGuard guard(a.device());
+  tb::GemmProblem p;
+  p.G = static_cast<int>(a.size(0));
+  p.M = static_cast<int>(a_mn ? a.size(2) : a.size(1));
+  p.K = static_cast<int>(a_mn ? a.size(1) : a.size(2));
+  p.N = static_cast<int>(b_mn ? b.size(2) : b.size(1));
+  TORCH_CHECK((b_mn ? b.size(1) : b.size(2)) == p.K, "tutel_b200.gemm: K mismatch");
+  TORCH_CHECK(d.size(0) == p.G && d.size(1) == p.M && d.size(2) == p.N, "tutel_b200.gemm: output shape mismatch");
+  p.b_group_div = static_cast<int>(b_group_div > 0 ? b_group_div : 1);
+  TORCH_CHECK(b.size(0) * p.b_group_div >= p.G, "tutel_b200.gemm: not enough B groups");
+  p.a = a.data_ptr(); p.lda = a.stride(1); p.a_group_stride = a.stride(0); p.a_mn_major = a_mn;
+  p.b = b.data_ptr(); p.ldb = b.stride(1); p.b_group_stride = b.stride(0); p.b_mn_major = b_mn;
+  p.in_dtype = gemm_dtype_of(a);
+  p.d = d.data_ptr(); p.ldd = d.stride(1); p.d_group_stride = d.stride(0);
+  p.out_dtype = gemm_dtype_of(d);
+  TORCH_CHECK(p.out_dtype <= tb::DT_FP32, "tutel_b200.gemm: output must be bf16/fp16/fp32");
+  p.epilogue = static_cast<int>(epilogue);
+  p.alpha = static_cast<float>(alpha);
+  if (bias.has_value() && bias->defined()) {
+    TORCH_CHECK(bias->is_cuda() && bias->scalar_type() == a.scalar_type() && bias->dim() == 2 && bias->stride(1) == 1,
+                "tutel_b200.gemm: bias must be [Gb, N] of the input dtype");
+    p.bias = bias->data_ptr();
+    p.bias_group_stride = bias->stride(0);
+  }
+  if (aux.has_value() && aux->defined()) {
+    TORCH_CHECK(aux->is_cuda() && aux->scalar_type() == d.scalar_type() && aux->dim() == 3 && aux->stride(2) == 1,
+                "tutel_b200.gemm: aux must be [G, M, N] of the output dtype");
+    p.aux = aux->data_ptr();
+    p.ld_aux = aux->stride(1);
+    p.aux_group_stride = aux->stride(0);
+  }
+  if (row_counts.has_value() && row_counts->defined()) {
+    TORCH_CHECK(row_counts->is_cuda() && row_counts->scalar_type() == at::kInt && row_counts->numel() >= p.G);
+    p.row_counts = row_counts->data_ptr<int>();
+  }
+  p.cta_group = static_cast<int>(cta_group);
+  p.block_n = static_cast<int>(block_n);
+  p.max_ctas = static_cast<int>(max_ctas);
+  p.d_ptr_table = reinterpret_cast<const unsigned long long*>(d_ptr_table);
+  p.signal_ptr_table = reinterpret_cast<const unsigned long long*>(signal_ptr_table);
+  p.wait_flags = reinterpret_cast<const uint32_t*>(wait_flags);
+  p.wait_rows_per_flag = static_cast<int>(wait_rows_per_flag);
+  p.wait_flags_per_group = static_cast<int>(wait_flags_per_group);
+  p.wait_target = static_cast<uint32_t>(wait_target);
+  const char* why = nullptr;
+  cudaError_t e = tb::gemm_sm100_launch(p, cur_stream(), &why);
+  TORCH_CHECK(e == cudaSuccess, "tutel_b200.gemm launch failed: ", why ? why : cudaGetErrorString(e));
+}
+
+std::vector<at::Tensor> route_locations(const at::Tensor& idx, int64_t E, int64_t C) {
+  TORCH_CHECK(idx.is_cuda() && idx.scalar_type() == at::kInt && idx.dim() == 2 && idx.is_contiguous());
+  const c10::cuda::CUDAGuard guard(idx.device());
+  const int k = static_cast<int>(idx.size(0)), S = static_cast<int>(idx.size(1));
+  auto opts = idx.options();
+  at::Tensor loc = at::empty({k, S}, opts);
+  at::Tensor counts = at::empty({E}, opts);
+  at::Tensor ws = at::empty({static_cast<int64_t>(tb::route_workspace_ints(S, static_cast<int>(E), k))}, opts);
+  TB_CHECK_CUDA(tb::route_locations(idx.data_ptr<int>(), loc.data_ptr<int>(), counts.data_ptr<int>(),
+                                    ws.data_ptr<int>(), S, static_cast<int>(E), k, cur_stream()));
+  std::vector<at::Tensor> out{loc, counts};
+  if (C > 0) {
+    at::Tensor slot = at::empty({E * C}, opts);
+    TB_CHECK_CUDA(tb::build_slot_map(idx.data_ptr<int>(), loc.data_ptr<int>(), slot.data_ptr<int>(), S,
+                                     static_cast<int>(E), k, static_cast<int>(C), cur_stream()));
+    out.push_back(slot);
+  }
+  return out;
+}
+
+at::Tensor build_slot_map(const at::Tensor& idx, const at::Tensor& loc, int64_t E, int64_t C) {
+  TORCH_CHECK(idx.is_cuda() && loc.is_cuda() && idx.scalar_type() == at::kInt && loc.scalar_type() == at::kInt);
+  TORCH_CHECK(idx.is_contiguous() && loc.is_contiguous() && idx.dim() == 2);
+  const c10::cuda::CUDAGuard guard(idx.device());
+  at::Tensor slot = at::empty({E * C}, idx.options());
+  TB_CHECK_CUDA(tb::build_slot_map(idx.data_ptr<int>(), loc.data_ptr<int>(), slot.data_ptr<int>(),
+                                   static_cast<int>(idx.size(1)), static_cast<int>(E), static_cast<int>(idx.size(0)),
+                                   static_cast<int>(C), cur_stream()));
+  return slot;
+}
+
+// x [S, M]; gates float [k, S] or None; slot_src int [E*C]; out [E*C, M] (ignored rows live in dst_ptr_table).
+void encode_rows(const at::Tensor& x, const c10::optional<at::Tensor>& gates, const at::Tensor& slot_src,
+                 at::Tensor& out, int64_t k, int64_t E, int64_t C, int64_t dst_ptr_table, int64_t signal_ptr_table,
+                 int64_t signal_rows, int64_t rot_chunks) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous() && slot_src.is_cuda() && slot_src.is_contiguous());
+  TORCH_CHECK(slot_src.scalar_type() == at::kInt && slot_src.numel() == E * C);
+  const c10::cuda::CUDAGuard guard(x.device());
+  const void* g = nullptr;
+  if (gates.has_value() && gates->defined()) {
+    TORCH_CHECK(gates->is_cuda() && gates->scalar_type() == at::kFloat && gates->is_contiguous());
+    g = gates->data_ptr();
+  }
+  if (dst_ptr_table == 0)
+    TORCH_CHECK(out.is_cuda() && out.is_contiguous() && out.scalar_type() == x.scalar_type() &&
+                out.numel() == E * C * x.size(1));
+  TB_CHECK_CUDA(tb::encode_rows(x.data_ptr(), g, slot_src.data_ptr<int>(), out.data_ptr(),
+                                reinterpret_cast<const unsigned long long*>(dst_ptr_table),
+                                reinterpret_cast<const unsigned long long*>(signal_ptr_table),
+                                static_cast<int>(signal_rows), static_cast<int>(x.size(0)), static_cast<int>(E),
+                                static_cast<int>(k), static_cast<int>(C), static_cast<int>(x.size(1)), elem_type_of(x),
+                                static_cast<int>(rot_chunks), 0, cur_stream()));
+}
+
+// buf [E*C, M]; gates float [k, S] or None; idx/loc int [k, S]; returns [S, M]
+at::Tensor decode_rows(const at::Tensor& buf, const c10::optional<at::Tensor>& gates, const at::Tensor& idx,
+                       const at::Tensor& loc, int64_t E, int64_t C, int64_t wait_flags, int64_t wait_target) {
+  TORCH_CHECK(buf.is_cuda() && buf.is_contiguous() && idx.is_cuda() && loc.is_cuda());
+  TORCH_CHECK(idx.scalar_type() == at::kInt && loc.scalar_type() == at::kInt && idx.is_contiguous() && loc.is_contiguous());
+  const c10::cuda::CUDAGuard guard(buf.device());
+  const int k = static_cast<int>(idx.size(0)), S = static_cast<int>(idx.size(1));
+  const int M = static_cast<int>(buf.numel() / (E * C));
+  const void* g = nullptr;
+  if (gates.has_value() && gates->defined()) {
+    TORCH_CHECK(gates->is_cuda() && gates->scalar_type() == at::kFloat && gates->is_contiguous());
+    g = gates->data_ptr();
+  }
+  at::Tensor out = at::empty({S, M}, buf.options());
+  TB_CHECK_CUDA(tb::decode_rows(buf.data_ptr(), g, idx.data_ptr<int>(), loc.data_ptr<int>(), out.data_ptr(),
+                                reinterpret_cast<const uint32_t*>(wait_flags), static_cast<uint32_t>(wait_target), S,
+                                static_cast<int>(E), k, static_cast<int>(C), M, elem_type_of(buf), cur_stream()));
+  return out;
+}
+
+// a [S, M], buf [E*C, M] -> float [k, S]
+at::Tensor gate_grad(const at::Tensor& a, const at::Tensor& buf, const at::Tensor& idx, const at::Tensor& loc,
+                     int64_t E, int64_t C) {
+  TORCH_CHECK(a.is_cuda() && a.is_contiguous() && buf.is_cuda() && buf.is_contiguous());
+  TORCH_CHECK(a.scalar_type() == buf.scalar_type());
+  const c10::cuda::CUDAGuard guard(a.device());
+  const int k = static_cast<int>(idx.size(0)), S = static_cast<int>(idx.size(1));
+  at::Tensor out = at::empty({k, S}, a.options().dtype(at::kFloat));
+  TB_CHECK_CUDA(tb::gate_grad(a.data_ptr(), buf.data_ptr(), idx.data_ptr<int>(), loc.data_ptr<int>(), out.data_ptr(),
+                              S, static_cast<int>(E), k, static_cast<int>(C), static_cast<int>(a.size(1)),
+                              elem_type_of(a), cur_stream()));
+  return out;
+}
+
+std::vector<at::Tensor> gate_topk_forward(const at::Tensor& logits, int64_t k) {
+  TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == at::kFloat && logits.dim() == 2 && logits.is_contiguous());
+  const c10::cuda::CUDAGuard guard(logits.device());
+  const int S = static_cast<int>(logits.size(0)), E = static_cast<int>(logits.size(1));
+  const int nblk = (S + 255) / 256;
+  at::Tensor scores = at::empty_like(logits);
+  at::Tensor idx = at::empty({k, S}, logits.options().dtype(at::kInt));
+  at::Tensor top = at::empty({k, S}, logits.options());
+  at::Tensor me = at::empty({nblk, E}, logits.options());
+  at::Tensor ce = at::empty({nblk, E}, logits.options().dtype(at::kInt));
+  TB_CHECK_CUDA(tb::gate_topk_forward(logits.data_ptr<float>(), scores.data_ptr<float>(), idx.data_ptr<int>(),
+                                      top.data_ptr<float>(), me.data_ptr<float>(), ce.data_ptr<int>(), S, E,
+                                      static_cast<int>(k), cur_stream()));
+  return {scores, idx, top, me, ce};
+}
+
+}  // namespace
+
+void register_symm_bindings(pybind11::module& m);  // symm_heap.cpp / p2p bindings
+void register_cpu_bindings(pybind11::module& m);   // cpu_kernels.cpp
+void register_jit_bindings(pybind11::module& m);   // jit_nvrtc.cpp
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "tutel_b200 native runtime: sm_100a tcgen05 grouped GEMM, routing/dispatch kernels, symmetric heap, "
+            "P2P collectives, NVRTC JIT";
+  m.def("gemm", &gemm);
+  m.def("route_locations", &route_locations);
+  m.def("build_slot_map", &build_slot_map);
+  m.def("encode_rows", &encode_rows);
+  m.def("decode_rows", &decode_rows);
+  m.def("gate_grad", &gate_grad);
+  m.def("gate_topk_forward", &gate_topk_forward);
+  register_symm_bindings(m);
+  register_cpu_bindings(m);
+  register_jit_bindings(m);
+}

@@ -1,0 +1,616 @@
+// tcgen05 / TMEM / TMA grouped GEMM for sm_100a (B200).
+//
+// Replaces the reference's cuBLAS `torch.matmul` expert GEMMs (tutel/experts/ffn.py:114-118,
+// tutel/experts/llama_ffn.py:38-41) and its host-synchronised per-expert loop
+// `sparse_bmm_infer` (tutel/custom/custom_kernel.cpp:874-889) with ONE persistent, warp-specialised kernel:
+//
+//   warp 0      TMA producer   cp.async.bulk.tensor (128B swizzle) -> smem ring, mbarrier complete_tx
+//   warp 1      MMA issuer     one thread issues tcgen05.mma (kind::f16 / kind::f8f6f4), accumulators in TMEM,
+//                              tcgen05.commit releases smem slots / publishes the accumulator
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue       tcgen05.ld TMEM->registers, fused bias/activation/activation-grad, 16-byte
+//                              global stores - optionally straight into PEER GPUs' memory plus a release.sys
+//                              counter bump (GEMM -> combine all-to-all fusion), while the MMA warp already
+//                              works on the next tile in the second TMEM accumulator buffer.
+//
+// The producer can also acquire system-scope "rows have arrived" counters before loading an A tile, which is
+// how the dispatch all-to-all is overlapped tile-by-tile with the first expert GEMM.
+//
+// CTA_GROUP == 2 runs CTA pairs (cluster of 2) with tcgen05.mma.cta_group::2 (UMMA_M = 256): each CTA stages
+// half of A's rows and half of B's columns, halving shared-memory traffic per SM.
+#include "gemm_sm100.h"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cstdio>
+#include <mutex>
+
+#include "ptx.cuh"
+
+namespace tb {
+
+struct GemmArgs {
+  int M, N, K, G;
+  int b_group_div;
+  int tiles_m, tiles_n;
+  long long num_tiles;
+  uint32_t idesc;
+  int elt_bytes;
+
+  void* d;
+  long long ldd, d_group_stride;
+  const unsigned long long* d_ptr_table;
+  int out_dtype;
+
+  int epilogue;
+  float alpha;
+  const void* bias;
+  long long bias_group_stride;
+  int bias_is_fp32;
+  const void* aux;
+  long long ld_aux, aux_group_stride;
+
+  const int* row_counts;
+
+  const uint32_t* wait_flags;
+  int wait_rows_per_flag, wait_flags_per_group;
+  uint32_t wait_target;
+  const unsigned long long* signal_ptr_table;
+};
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kSwizzleBytes = 128;   // one swizzle row: 64 bf16 / 128 fp8
+constexpr int kBlockKRows = 64;      // k-rows per stage for MN-major 16-bit operands (== BK elements)
+constexpr int kSmemLimit = 232448;   // 227 KB
+
+template <int CG, int BN>
+struct Cfg {
+  static constexpr int BM_CTA = 128;
+  static constexpr int BM = 128 * CG;
+  static constexpr int BN_CTA = BN / CG;
+  static constexpr int A_BYTES = BM_CTA * kSwizzleBytes;
+  static constexpr int B_BYTES = BN_CTA * kSwizzleBytes;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int AUX_BYTES = 1024 /*align slack*/ + 512 /*barriers + tmem ptr*/;
+  static constexpr int STAGES_RAW = (kSmemLimit - AUX_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;  // double-buffered fp32 accumulator
+  static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
+  static_assert(STAGES >= 3, "need a real pipeline");
+};
+
+struct TileCoord {
+  int g, m_blk, n_blk;
+};
+
+// Tiles are enumerated group-major; inside a group, bands of kBand row-blocks sweep all column blocks so that a
+// wave of CTAs re-uses both its A band and its B columns out of L2.
+template <int kBand>
+__device__ __forceinline__ TileCoord decode_tile(long long t, int tiles_m, int tiles_n) {
+  const int per_group = tiles_m * tiles_n;
+  TileCoord c;
+  c.g = static_cast<int>(t / per_group);
+  int r = static_cast<int>(t - static_cast<long long>(c.g) * per_group);
+  const int band_tiles = kBand * tiles_n;
+  const int band = r / band_tiles;
+  const int first_m = band * kBand;
+  const int rows_in_band = min(kBand, tiles_m - first_m);
+  r -= band * band_tiles;
+  c.m_blk = first_m + r % rows_in_band;
+  c.n_blk = r / rows_in_band;
+  return c;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ void unpack8(const uint4& u, bool is_bf16, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (is_bf16) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    } else {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      const float2 t = __half22float2(h);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, bool is_bf16) {
+  if (is_bf16) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int CG, bool A_MN, bool B_MN, int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const GemmArgs args) {
+  using C = Cfg<CG, BN>;
+  extern __shared__ uint8_t smem_raw[];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+  const bool is_leader = (cta_rank == 0);
+
+  // ---- shared memory carve-up (operand ring must be 1024B aligned for the 128B swizzle) ----
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  auto smem_a = [&](int s) { return smem_base + s * C::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * C::STAGE_BYTES + C::A_BYTES; };
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tfull_bar(a), 1);
+      ptx::mbar_init(tempty_bar(a), 4 * CG);  // one arrival per epilogue warp of every CTA in the group
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<CG>(tmem_slot, C::TMEM_COLS);
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_kb = (args.K * args.elt_bytes + kSwizzleBytes - 1) / kSwizzleBytes;
+  const int bk_elems = kSwizzleBytes / args.elt_bytes;       // K elements per stage
+  const long long tile_step = gridDim.x / CG;
+  const long long tile_first = blockIdx.x / CG;
+  constexpr int kBand = (CG == 2) ? 8 : 16;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    int s = 0;
+    uint32_t ph = 0;
+    for (long long t = tile_first; t < args.num_tiles; t += tile_step) {
+      const TileCoord tc = decode_tile<kBand>(t, args.tiles_m, args.tiles_n);
+      if (args.row_counts != nullptr && tc.m_blk * C::BM >= args.row_counts[tc.g]) continue;
+      const int m0 = tc.m_blk * C::BM + static_cast<int>(cta_rank) * C::BM_CTA;
+      const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * C::BN_CTA;
+      const int gb = tc.g / args.b_group_div;
+      if (args.wait_flags != nullptr) {
+        // Dispatch fusion: rows of this tile are pushed by peer GPUs; wait for their release-counters.
+        if (lane == 0) {
+          const int f0 = (tc.m_blk * C::BM) / args.wait_rows_per_flag;
+          int f1 = (min(tc.m_blk * C::BM + C::BM, args.M) - 1) / args.wait_rows_per_flag;
+          for (int f = f0; f <= f1; ++f)
+            ptx::wait_flag_ge_sys(args.wait_flags + static_cast<long long>(tc.g) * args.wait_flags_per_group + f,
+                                  args.wait_target);
+          ptx::fence_proxy_async_global();  // order the upcoming async-proxy (TMA) reads after the acquire
+        }
+        __syncwarp();
+      }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+        if (ptx::elect_one()) {
+          const uint32_t fb = full_bar(s);
+          if constexpr (CG == 1) {
+            ptx::mbar_expect_tx(fb, C::STAGE_BYTES);
+          } else {
+            if (is_leader) ptx::mbar_expect_tx(fb, 2 * C::STAGE_BYTES);
+          }
+          const int k0 = kb * bk_elems;
+          // ---- A ----
+          if constexpr (!A_MN) {
+            if constexpr (CG == 1) ptx::tma_load_3d(smem_a(s), &tmA, fb, k0, m0, tc.g);
+            else ptx::tma_load_3d_2sm(smem_a(s), &tmA, fb, k0, m0, tc.g);
+          } else {
+            const int chunk_elems = kSwizzleBytes / args.elt_bytes;
+            const int chunk_bytes = bk_elems * kSwizzleBytes;
+            const int nchunk = C::BM_CTA / chunk_elems;
+            for (int c = 0; c < nchunk; ++c) {
+              if constexpr (CG == 1)
+                ptx::tma_load_3d(smem_a(s) + c * chunk_bytes, &tmA, fb, m0 + c * chunk_elems, k0, tc.g);
+              else
+                ptx::tma_load_3d_2sm(smem_a(s) + c * chunk_bytes, &tmA, fb, m0 + c * chunk_elems, k0, tc.g);
+            }
+          }
+          // ---- B ----
+          if constexpr (!B_MN) {
+            if constexpr (CG == 1) ptx::tma_load_3d(smem_b(s), &tmB, fb, k0, n0, gb);
+            else ptx::tma_load_3d_2sm(smem_b(s), &tmB, fb, k0, n0, gb);
+          } else {
+            const int chunk_elems = kSwizzleBytes / args.elt_bytes;
+            const int chunk_bytes = bk_elems * kSwizzleBytes;
+            const int nchunk = C::BN_CTA / chunk_elems;
+            for (int c = 0; c < nchunk; ++c) {
+              if constexpr (CG == 1)
+                ptx::tma_load_3d(smem_b(s) + c * chunk_bytes, &tmB, fb, n0 + c * chunk_elems, k0, gb);
+              else
+                ptx::tma_load_3d_2sm(smem_b(s) + c * chunk_bytes, &tmB, fb, n0 + c * chunk_elems, k0, gb);
+            }
+          }
+        }
+        __syncwarp();
+        if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (CG == 1 || is_leader) {
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      // Per-16/32-element K step inside one 128-byte swizzle row: +32 B (K-major) or +UMMA_K rows (MN-major).
+      const uint32_t mn_kstep_bytes = (32u / args.elt_bytes) * kSwizzleBytes;  // UMMA_K rows * 128 B
+      const uint32_t mn_chunk_bytes = static_cast<uint32_t>(bk_elems) * kSwizzleBytes;
+      const uint32_t a_lbo = A_MN ? mn_chunk_bytes : 16u;
+      const uint32_t b_lbo = B_MN ? mn_chunk_bytes : 16u;
+      const uint32_t a_kstep = A_MN ? mn_kstep_bytes : 32u;
+      const uint32_t b_kstep = B_MN ? mn_kstep_bytes : 32u;
+      for (long long t = tile_first; t < args.num_tiles; t += tile_step) {
+        const TileCoord tc = decode_tile<kBand>(t, args.tiles_m, args.tiles_n);
+        if (args.row_counts != nullptr && tc.m_blk * C::BM >= args.row_counts[tc.g]) continue;
+        ptx::mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(full_bar(s), ph);
+          ptx::tc_fence_after();
+          if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = ptx::make_smem_desc_sw128(smem_a(s) + k * a_kstep, a_lbo, 1024u);
+              const uint64_t bd = ptx::make_smem_desc_sw128(smem_b(s) + k * b_kstep, b_lbo, 1024u);
+              if (args.elt_bytes == 2) ptx::umma_f16<CG>(d_tmem, ad, bd, args.idesc, (kb | k) != 0);
+              else ptx::umma_f8<CG>(d_tmem, ad, bd, args.idesc, (kb | k) != 0);
+            }
+            ptx::umma_commit<CG>(empty_bar(s));                       // smem slot reusable once these retire
+            if (kb == num_kb - 1) ptx::umma_commit<CG>(tfull_bar(acc));  // accumulator complete
+          }
+          __syncwarp();
+          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+        }
+        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue ===============================
+    const int ew = warp - 4;  // == warp % 4: TMEM lane quarter this warp may touch
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    const bool out16 = (args.out_dtype != DT_FP32);
+    const bool out_bf16 = (args.out_dtype == DT_BF16);
+    for (long long t = tile_first; t < args.num_tiles; t += tile_step) {
+      const TileCoord tc = decode_tile<kBand>(t, args.tiles_m, args.tiles_n);
+      int m_valid = args.M;
+      if (args.row_counts != nullptr) {
+        m_valid = min(args.M, args.row_counts[tc.g]);
+        if (tc.m_blk * C::BM >= m_valid) continue;
+      }
+      const int m = tc.m_blk * C::BM + static_cast<int>(cta_rank) * C::BM_CTA + ew * 32 + lane;
+      const bool row_ok = m < m_valid;
+      const int gb = tc.g / args.b_group_div;
+      uint8_t* d_base = (args.d_ptr_table != nullptr)
+                            ? reinterpret_cast<uint8_t*>(args.d_ptr_table[tc.g])
+                            : reinterpret_cast<uint8_t*>(args.d) +
+                                  static_cast<long long>(tc.g) * args.d_group_stride * (out16 ? 2 : 4);
+      uint8_t* d_row = d_base + static_cast<long long>(m) * args.ldd * (out16 ? 2 : 4);
+      const uint8_t* aux_row = nullptr;
+      if (args.aux != nullptr)
+        aux_row = reinterpret_cast<const uint8_t*>(args.aux) +
+                  (static_cast<long long>(tc.g) * args.aux_group_stride + static_cast<long long>(m) * args.ld_aux) * 2;
+      const uint8_t* bias_g = nullptr;
+      if (args.bias != nullptr)
+        bias_g = reinterpret_cast<const uint8_t*>(args.bias) +
+                 static_cast<long long>(gb) * args.bias_group_stride * (args.bias_is_fp32 ? 4 : 2);
+
+      ptx::mbar_wait(tfull_bar(acc), acc_ph);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(ew * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n = tc.n_blk * BN + c * 32;
+        if (n >= args.N) break;  // warp-uniform
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(t_row + static_cast<uint32_t>(c * 32), r);
+        ptx::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const int ncols = min(32, args.N - n);  // multiple of 8
+
+        if (args.epilogue == EPI_NONE) {
+          if (args.alpha != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= args.alpha;
+          }
+        } else if (args.epilogue == EPI_RELU_BWD) {
+          if (row_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q * 8 < ncols) {
+                float f[8];
+                unpack8(ptx::ld_nc_v4(aux_row + (n + q * 8) * 2), out_bf16, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[q * 8 + j] = f[j] > 0.0f ? v[q * 8 + j] : 0.0f;
+              }
+            }
+          }
+        } else {
+          if (bias_g != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q * 8 < ncols) {
+                float f[8];
+                if (args.bias_is_fp32) {
+                  const float4 b0 = *reinterpret_cast<const float4*>(bias_g + (n + q * 8) * 4);
+                  const float4 b1 = *reinterpret_cast<const float4*>(bias_g + (n + q * 8 + 4) * 4);
+                  f[0] = b0.x; f[1] = b0.y; f[2] = b0.z; f[3] = b0.w;
+                  f[4] = b1.x; f[5] = b1.y; f[6] = b1.z; f[7] = b1.w;
+                } else {
+                  unpack8(*reinterpret_cast<const uint4*>(bias_g + (n + q * 8) * 2), args.elt_bytes == 2
+                              ? ((args.idesc >> 7) & 7u) == 1u
+                              : out_bf16, f);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
+              }
+            }
+          }
+          if (args.epilogue == EPI_BIAS_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+          } else if (args.epilogue == EPI_BIAS_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (args.epilogue == EPI_BIAS_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+          }
+        }
+
+        if (row_ok) {
+          if (out16) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q * 8 < ncols) {
+                uint4 o;
+                o.x = pack2(v[q * 8 + 0], v[q * 8 + 1], out_bf16);
+                o.y = pack2(v[q * 8 + 2], v[q * 8 + 3], out_bf16);
+                o.z = pack2(v[q * 8 + 4], v[q * 8 + 5], out_bf16);
+                o.w = pack2(v[q * 8 + 6], v[q * 8 + 7], out_bf16);
+                *reinterpret_cast<uint4*>(d_row + (n + q * 8) * 2) = o;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (q * 4 < ncols) {
+                float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                *reinterpret_cast<float4*>(d_row + (n + q * 4) * 4) = o;
+              }
+            }
+          }
+        }
+      }
+      // Accumulator drained: hand the TMEM buffer back to the MMA warp.
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 1) ptx::mbar_arrive(tempty_bar(acc));
+        else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);
+      }
+      if (args.signal_ptr_table != nullptr) {
+        // Combine fusion: all 128 epilogue threads' (possibly remote) stores -> one release.sys counter bump.
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (ew == 0 && lane == 0) {
+          ptx::fence_acq_rel_sys();
+          ptx::red_add_release_sys(reinterpret_cast<uint32_t*>(args.signal_ptr_table[tc.g]), 1u);
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+    }
+  }
+
+  // ---- teardown ----
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+bool make_operand_map(CUtensorMap* map, const void* base, int dtype, bool mn_major, long long rows_mn,
+                      long long k, long long ld, long long group_stride, int groups, int box_mn_kmajor,
+                      const char** why) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) { *why = "cuTensorMapEncodeTiled unavailable"; return false; }
+  const int eb = (dtype == DT_E4M3 || dtype == DT_E5M2) ? 1 : 2;
+  CUtensorMapDataType dt = eb == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                   : (dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * eb) & 15) || ((group_stride * eb) & 15)) {
+    *why = "operand base/stride must be 16-byte aligned";
+    return false;
+  }
+  cuuint64_t dims[3];
+  cuuint64_t strides[2];
+  cuuint32_t box[3];
+  cuuint32_t estr[3] = {1, 1, 1};
+  const cuuint32_t row_elems = kSwizzleBytes / eb;
+  if (!mn_major) {
+    dims[0] = static_cast<cuuint64_t>(k); dims[1] = static_cast<cuuint64_t>(rows_mn);
+    box[0] = row_elems; box[1] = static_cast<cuuint32_t>(box_mn_kmajor);
+  } else {
+    dims[0] = static_cast<cuuint64_t>(rows_mn); dims[1] = static_cast<cuuint64_t>(k);
+    box[0] = row_elems; box[1] = row_elems;  // BK k-rows x one 128-byte MN chunk
+  }
+  dims[2] = static_cast<cuuint64_t>(groups);
+  box[2] = 1;
+  strides[0] = static_cast<cuuint64_t>(ld) * eb;
+  strides[1] = static_cast<cuuint64_t>(groups > 1 ? group_stride : (mn_major ? k : rows_mn) * ld) * eb;
+  if (strides[1] == 0) strides[1] = strides[0];
+  CUresult r = enc(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { *why = "cuTensorMapEncodeTiled failed"; return false; }
+  return true;
+}
+
+uint32_t make_idesc(int in_dtype, bool a_mn, bool b_mn, int umma_m, int umma_n) {
+  uint32_t fmt;
+  switch (in_dtype) {
+    case DT_BF16: fmt = 1; break;
+    case DT_FP16: fmt = 0; break;
+    case DT_E4M3: fmt = 0; break;
+    default: fmt = 1; break;  // DT_E5M2
+  }
+  uint32_t d = 0;
+  d |= 1u << 4;                       // accumulator format: fp32
+  d |= fmt << 7;                      // A format
+  d |= fmt << 10;                     // B format
+  d |= (a_mn ? 1u : 0u) << 15;        // A major
+  d |= (b_mn ? 1u : 0u) << 16;        // B major
+  d |= static_cast<uint32_t>(umma_n >> 3) << 17;
+  d |= static_cast<uint32_t>(umma_m >> 4) << 24;
+  return d;
+}
+
+template <int CG, bool A_MN, bool B_MN, int BN>
+cudaError_t launch_inst(const CUtensorMap& ta, const CUtensorMap& tb_, const GemmArgs& args, int grid,
+                        cudaStream_t stream) {
+  using C = Cfg<CG, BN>;
+  auto* kern = gemm_sm100_kernel<CG, A_MN, B_MN, BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb_, args);
+}
+
+}  // namespace
+
+cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const char** why_out) {
+  const char* why_local = nullptr;
+  const char** why = why_out ? why_out : &why_local;
+  *why = nullptr;
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.G <= 0) return cudaSuccess;
+  const int eb = (p.in_dtype == DT_E4M3 || p.in_dtype == DT_E5M2) ? 1 : 2;
+  if (p.N % 8 != 0) { *why = "N must be a multiple of 8"; return cudaErrorInvalidValue; }
+  const int ob = p.out_dtype == DT_FP32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(p.d) & 15) || ((p.ldd * ob) & 15) || ((p.d_group_stride * ob) & 15)) {
+    *why = "output base/stride must be 16-byte aligned";
+    return cudaErrorInvalidValue;
+  }
+
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static int sm_count_cache[64] = {0};
+  if (sm_count_cache[dev & 63] == 0) cudaDeviceGetAttribute(&sm_count_cache[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+  int sms = sm_count_cache[dev & 63];
+  if (p.max_ctas > 0) sms = p.max_ctas < sms ? p.max_ctas : sms;
+
+  int cg = p.cta_group;
+  int bn = p.block_n;
+  if (bn == 0) bn = (p.N <= 128) ? 128 : 256;
+  if (cg == 0) cg = (p.M > 128) ? 2 : 1;
+  if (cg == 2 && (sms & 1)) sms -= 1;
+
+  const int bm = 128 * cg;
+  GemmArgs a{};
+  a.M = p.M; a.N = p.N; a.K = p.K; a.G = p.G;
+  a.b_group_div = p.b_group_div > 0 ? p.b_group_div : 1;
+  a.tiles_m = (p.M + bm - 1) / bm;
+  a.tiles_n = (p.N + bn - 1) / bn;
+  a.num_tiles = static_cast<long long>(a.tiles_m) * a.tiles_n * p.G;
+  a.idesc = make_idesc(p.in_dtype, p.a_mn_major, p.b_mn_major, bm, bn);
+  a.elt_bytes = eb;
+  a.d = p.d; a.ldd = p.ldd; a.d_group_stride = p.d_group_stride; a.d_ptr_table = p.d_ptr_table;
+  a.out_dtype = p.out_dtype;
+  a.epilogue = p.epilogue; a.alpha = p.alpha;
+  a.bias = p.bias; a.bias_group_stride = p.bias_group_stride; a.bias_is_fp32 = 0;
+  a.aux = p.aux; a.ld_aux = p.ld_aux; a.aux_group_stride = p.aux_group_stride;
+  a.row_counts = p.row_counts;
+  a.wait_flags = p.wait_flags; a.wait_rows_per_flag = p.wait_rows_per_flag > 0 ? p.wait_rows_per_flag : bm;
+  a.wait_flags_per_group = p.wait_flags_per_group; a.wait_target = p.wait_target;
+  a.signal_ptr_table = p.signal_ptr_table;
+
+  CUtensorMap ta, tb_;
+  const int gB = (p.G + a.b_group_div - 1) / a.b_group_div;
+  if (!make_operand_map(&ta, p.a, p.in_dtype, p.a_mn_major, p.M, p.K, p.lda, p.a_group_stride, p.G, 128, why))
+    return cudaErrorInvalidValue;
+  if (!make_operand_map(&tb_, p.b, p.in_dtype, p.b_mn_major, p.N, p.K, p.ldb, p.b_group_stride, gB, bn / cg, why))
+    return cudaErrorInvalidValue;
+
+  long long want = a.num_tiles * cg;
+  int grid = static_cast<int>(want < sms ? want : sms);
+  if (cg == 2 && (grid & 1)) grid += 1;
+
+#define TB_LAUNCH(CGv, AMN, BMN, BNv) return launch_inst<CGv, AMN, BMN, BNv>(ta, tb_, a, grid, stream)
+#define TB_SWITCH_MAJOR(CGv, BNv)                                    \
+  do {                                                               \
+    if (!p.a_mn_major && !p.b_mn_major) TB_LAUNCH(CGv, false, false, BNv); \
+    if (!p.a_mn_major && p.b_mn_major) TB_LAUNCH(CGv, false, true, BNv);   \
+    if (p.a_mn_major && !p.b_mn_major) TB_LAUNCH(CGv, true, false, BNv);   \
+    TB_LAUNCH(CGv, true, true, BNv);                                       \
+  } while (0)
+  if (cg == 1 && bn == 256) TB_SWITCH_MAJOR(1, 256);
+  if (cg == 1 && bn == 128) TB_SWITCH_MAJOR(1, 128);
+  if (cg == 2 && bn == 256) TB_SWITCH_MAJOR(2, 256);
+  if (cg == 2 && bn == 128) TB_SWITCH_MAJOR(2, 128);
+#undef TB_SWITCH_MAJOR
+#undef TB_LAUNCH
+  *why = "unsupported cta_group/block_n";
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace tb

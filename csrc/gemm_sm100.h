@@ -1,0 +1,74 @@
+// Host API of the sm_100a tcgen05 grouped GEMM family (see gemm_sm100.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tb {
+
+enum GemmEpilogue : int {
+  EPI_NONE = 0,       // D = acc * alpha
+  EPI_BIAS = 1,       // D = acc + bias[n]
+  EPI_BIAS_RELU = 2,  // D = relu(acc + bias[n])        (bias optional)
+  EPI_BIAS_GELU = 3,  // D = gelu_erf(acc + bias[n])
+  EPI_BIAS_SILU = 4,  // D = silu(acc + bias[n])
+  EPI_RELU_BWD = 5,   // D = aux[m,n] > 0 ? acc : 0     (aux = forward activation output)
+};
+
+enum GemmDtype : int { DT_BF16 = 0, DT_FP16 = 1, DT_FP32 = 2, DT_E4M3 = 3, DT_E5M2 = 4 };
+
+// One launch computes, for every group g in [0,G):
+//     D_g[M,N] = epilogue( A_g[M,K] * B_{g / b_group_div}[K,N] )
+// A is "K-major" when element (m,k) is at a + m*lda + k, "MN-major" when it is at a + k*lda + m.
+// B is "K-major" when element (k,n) is at b + n*ldb + k (i.e. an [N,K] row-major weight), "MN-major" when at
+// b + k*ldb + n ([K,N] row-major).  D is always row-major [M,N].
+struct GemmProblem {
+  int M = 0, N = 0, K = 0, G = 1;
+  int b_group_div = 1;
+
+  const void* a = nullptr;
+  long long lda = 0, a_group_stride = 0;  // in elements
+  bool a_mn_major = false;
+  const void* b = nullptr;
+  long long ldb = 0, b_group_stride = 0;
+  bool b_mn_major = false;
+  int in_dtype = DT_BF16;  // A and B element type
+
+  void* d = nullptr;
+  long long ldd = 0, d_group_stride = 0;
+  int out_dtype = DT_BF16;
+  // Optional: per-group output base pointers (device array of G uint64). Entries may point into PEER GPUs'
+  // memory (NVLink P2P mapping): this is how the GEMM->combine all-to-all is fused into the epilogue.
+  const unsigned long long* d_ptr_table = nullptr;
+
+  int epilogue = EPI_NONE;
+  float alpha = 1.0f;
+  const void* bias = nullptr;  // [G / b_group_div, N], same dtype as A/B
+  long long bias_group_stride = 0;
+  const void* aux = nullptr;  // [G, M, N] row-major, out_dtype
+  long long ld_aux = 0, aux_group_stride = 0;
+
+  // Optional: valid rows per group (device int32[G]); row tiles past the count are skipped entirely
+  // (dropless / Megablocks path: no host sync, no padded FLOPs).
+  const int* row_counts = nullptr;
+
+  // Optional dispatch fusion: before the A rows [m0, m0+BM) of group g are loaded, the TMA producer
+  // acquires  wait_flags[g * wait_flags_per_group + m0 / wait_rows_per_flag] >= wait_target  (system scope);
+  // peers bump these counters after pushing token rows over NVLink.
+  const uint32_t* wait_flags = nullptr;
+  int wait_rows_per_flag = 0, wait_flags_per_group = 0;
+  uint32_t wait_target = 0;
+  // Optional combine fusion: after an output tile of group g is stored, signal_ptr_table[g] (a uint32 counter,
+  // usually in a peer's memory) is incremented with release.sys semantics.
+  const unsigned long long* signal_ptr_table = nullptr;
+
+  // Tuning: cta_group (1 or 2, 0 = auto), BN (128 or 256, 0 = auto)
+  int cta_group = 0;
+  int block_n = 0;
+  int max_ctas = 0;  // 0 = all SMs
+};
+
+// Returns cudaSuccess or the launch error; throws nothing.  `why` (optional) receives a static message on
+// argument errors (misaligned strides etc.).
+cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const char** why = nullptr);
+
+}  // namespace tb

@@ -1,0 +1,180 @@
+#include "jit_nvrtc.h"
+
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <torch/extension.h>
+
+#include <map>
+#include <mutex>
+#include <regex>
+#include <string>
+#include <vector>
+
+namespace {
+
+// ---- minimal NVRTC surface, resolved at first use ----
+using nvrtcProgram = struct _nvrtcProgram*;
+struct Nvrtc {
+  int (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
+  int (*CompileProgram)(nvrtcProgram, int, const char* const*);
+  int (*GetProgramLogSize)(nvrtcProgram, size_t*);
+  int (*GetProgramLog)(nvrtcProgram, char*);
+  int (*GetCUBINSize)(nvrtcProgram, size_t*);
+  int (*GetCUBIN)(nvrtcProgram, char*);
+  int (*GetPTXSize)(nvrtcProgram, size_t*);
+  int (*GetPTX)(nvrtcProgram, char*);
+  int (*DestroyProgram)(nvrtcProgram*);
+  bool ok = false;
+};
+
+Nvrtc& nvrtc() {
+  static Nvrtc n;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                           "/usr/local/cuda/lib64/libnvrtc.so"};
+    void* h = nullptr;
+    for (const char* nm : names) {
+      h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (h) break;
+    }
+    if (!h) return;
+#define TB_SYM(field, sym) n.field = reinterpret_cast<decltype(n.field)>(dlsym(h, sym)); if (!n.field) return;
+    TB_SYM(CreateProgram, "nvrtcCreateProgram")
+    TB_SYM(CompileProgram, "nvrtcCompileProgram")
+    TB_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+    TB_SYM(GetProgramLog, "nvrtcGetProgramLog")
+    TB_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+    TB_SYM(GetCUBIN, "nvrtcGetCUBIN")
+    TB_SYM(GetPTXSize, "nvrtcGetPTXSize")
+    TB_SYM(GetPTX, "nvrtcGetPTX")
+    TB_SYM(DestroyProgram, "nvrtcDestroyProgram")
+#undef TB_SYM
+    n.ok = true;
+  });
+  return n;
+}
+
+struct JitKernel {
+  std::string source;
+  std::string entry;
+  int grid[3] = {1, 1, 1};
+  int block[3] = {1, 1, 1};
+  std::map<int, cudaKernel_t> per_device;
+};
+
+std::vector<JitKernel>& registry() {
+  static std::vector<JitKernel> r;
+  return r;
+}
+std::mutex& reg_mutex() {
+  static std::mutex m;
+  return m;
+}
+
+// `// [thread_extent] blockIdx.x = 512` style launch annotations, as in the reference's kernel strings.
+void parse_extents(JitKernel& k) {
+  std::regex re(R"(\[thread_extent\]\s*(blockIdx|threadIdx)\.([xyz])\s*=\s*(\d+))");
+  for (auto it = std::sregex_iterator(k.source.begin(), k.source.end(), re); it != std::sregex_iterator(); ++it) {
+    const int axis = (*it)[2].str()[0] - 'x';
+    const int v = std::stoi((*it)[3].str());
+    if ((*it)[1].str() == "blockIdx") k.grid[axis] = v; else k.block[axis] = v;
+  }
+  std::smatch m;
+  std::regex ent(R"(__global__\s+(?:__launch_bounds__\s*\([^)]*\)\s*)?void\s+(\w+)\s*\()");
+  if (std::regex_search(k.source, m, ent)) k.entry = m[1].str();
+  TORCH_CHECK(!k.entry.empty(), "tutel_b200.jit: no `__global__ void NAME(` entry point found in source");
+}
+
+cudaKernel_t activate(JitKernel& k, int device) {
+  auto it = k.per_device.find(device);
+  if (it != k.per_device.end()) return it->second;
+  Nvrtc& n = nvrtc();
+  TORCH_CHECK(n.ok, "tutel_b200.jit: libnvrtc could not be loaded");
+  cudaDeviceProp prop;
+  TORCH_CHECK(cudaGetDeviceProperties(&prop, device) == cudaSuccess);
+  std::string arch = "--gpu-architecture=sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+  if (prop.major >= 9) arch += "a";
+  std::string src = k.source;
+  if (src.find("extern \"C\"") == std::string::npos) {
+    // give the entry point C linkage so that it can be looked up by name
+    const std::string needle = "__global__";
+    const size_t pos = src.find(needle);
+    if (pos != std::string::npos) src.insert(pos, "extern \"C\" ");
+  }
+  nvrtcProgram prog = nullptr;
+  TORCH_CHECK(n.CreateProgram(&prog, src.c_str(), "tutel_b200_jit.cu", 0, nullptr, nullptr) == 0);
+  const char* opts[] = {arch.c_str(), "--std=c++17", "-default-device", "--include-path=/usr/local/cuda/include"};
+  const int rc = n.CompileProgram(prog, 4, opts);
+  if (rc != 0) {
+    size_t ls = 0;
+    n.GetProgramLogSize(prog, &ls);
+    std::string log(ls, '\0');
+    n.GetProgramLog(prog, log.data());
+    n.DestroyProgram(&prog);
+    TORCH_CHECK(false, "tutel_b200.jit: NVRTC compilation failed:\n", log);
+  }
+  size_t sz = 0;
+  TORCH_CHECK(n.GetCUBINSize(prog, &sz) == 0 && sz > 0, "tutel_b200.jit: no CUBIN produced");
+  std::string image(sz, '\0');
+  TORCH_CHECK(n.GetCUBIN(prog, image.data()) == 0);
+  n.DestroyProgram(&prog);
+  cudaLibrary_t lib;
+  TORCH_CHECK(cudaLibraryLoadData(&lib, image.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess,
+              "tutel_b200.jit: cudaLibraryLoadData failed");
+  cudaKernel_t kern;
+  TORCH_CHECK(cudaLibraryGetKernel(&kern, lib, k.entry.c_str()) == cudaSuccess,
+              "tutel_b200.jit: entry point not found: ", k.entry);
+  k.per_device[device] = kern;
+  return kern;
+}
+
+int64_t inject_source(const std::string& source) {
+  std::lock_guard<std::mutex> g(reg_mutex());
+  JitKernel k;
+  k.source = source;
+  parse_extents(k);
+  registry().push_back(std::move(k));
+  return static_cast<int64_t>(registry().size()) - 1;
+}
+
+void invoke(const std::vector<at::Tensor>& tensors, const std::vector<int64_t>& extra, const std::vector<int64_t>& blocks,
+            int64_t handle) {
+  std::lock_guard<std::mutex> g(reg_mutex());
+  TORCH_CHECK(handle >= 0 && handle < static_cast<int64_t>(registry().size()), "tutel_b200.jit: bad kernel handle");
+  JitKernel& k = registry()[handle];
+  TORCH_CHECK(!tensors.empty() && tensors[0].is_cuda(), "tutel_b200.jit: first argument must be a CUDA tensor");
+  const int device = tensors[0].device().index();
+  const c10::cuda::CUDAGuard guard(tensors[0].device());
+  cudaKernel_t kern = activate(k, device);
+  std::vector<void*> ptrs(tensors.size());
+  std::vector<int> ints(extra.size());
+  std::vector<void*> args;
+  for (size_t i = 0; i < tensors.size(); ++i) {
+    TORCH_CHECK(tensors[i].is_cuda(), "tutel_b200.jit: all tensor arguments must be CUDA tensors");
+    ptrs[i] = tensors[i].data_ptr();
+    args.push_back(&ptrs[i]);
+  }
+  for (size_t i = 0; i < extra.size(); ++i) {
+    ints[i] = static_cast<int>(extra[i]);
+    args.push_back(&ints[i]);
+  }
+  dim3 grid(k.grid[0], k.grid[1], k.grid[2]), block(k.block[0], k.block[1], k.block[2]);
+  if (!blocks.empty()) {
+    grid = dim3(static_cast<unsigned>(blocks[0]), blocks.size() > 1 ? static_cast<unsigned>(blocks[1]) : 1,
+                blocks.size() > 2 ? static_cast<unsigned>(blocks[2]) : 1);
+  }
+  cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void*>(kern), grid, block, args.data(), 0,
+                                   at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(e == cudaSuccess, "tutel_b200.jit: launch failed: ", cudaGetErrorString(e));
+}
+
+}  // namespace
+
+void register_jit_bindings(pybind11::module& m) {
+  m.def("jit_inject_source", &inject_source);
+  m.def("jit_invoke", &invoke);
+  m.def("jit_available", [] { return nvrtc().ok; });
+}

@@ -1,0 +1,613 @@
+// Routing and sparse dispatch/combine kernels for sm_100a.
+//
+// Functional counterpart of the reference's SIMT JIT kernels (tutel/jit_kernels/sparse.py:17-134), its
+// `tutel_ops.cumsum` Blelloch scan (tutel/custom/custom_kernel.cpp:822-872) and the ~15 small torch kernels of
+// `extract_critical` (tutel/impls/fast_dispatch.py:143-204), re-designed slot-centrically:
+//
+//   * routing produces, besides idx/loc, an INVERSE map slot -> (token, choice).  Encode then becomes a fully
+//     coalesced row gather that also writes the zero padding (no separate zero-fill pass, one launch for all k,
+//     native bf16/fp16 - the reference up-casts bf16 to fp32 and launches k scatters);
+//   * encode can push rows straight into PEER GPUs' receive buffers (16-byte NVLink stores) and publish
+//     release.sys counters per row block - the dispatch all-to-all is fused into the scatter;
+//   * decode sums all k choices in one pass with fp32 accumulation and can acquire per-expert arrival counters
+//     (combine all-to-all fused into the GEMM epilogue on the producer side).
+#include "moe_kernels.h"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+
+namespace tb {
+namespace {
+
+constexpr int kRouteBlock = 1024;
+constexpr int kInvalidLoc = 0x3fffffff;
+
+// ------------------------------------------------------------------------------------------------
+// routing
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRouteBlock) route_hist_kernel(const int* __restrict__ idx, int* __restrict__ ws,
+                                                                int S, int E, int k) {
+  extern __shared__ int hist[];
+  const int b = blockIdx.x;
+  const int s = b * kRouteBlock + threadIdx.x;
+  for (int j = 0; j < k; ++j) {
+    for (int e = threadIdx.x; e < E; e += kRouteBlock) hist[e] = 0;
+    __syncthreads();
+    if (s < S) {
+      const int e = idx[static_cast<long long>(j) * S + s];
+      if (e >= 0 && e < E) atomicAdd(&hist[e], 1);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < E; e += kRouteBlock) ws[(static_cast<long long>(b) * k + j) * E + e] = hist[e];
+    __syncthreads();
+  }
+}
+
+// One thread per expert: exclusive prefix over (choice, block) in that order -> every block learns where its
+// tokens start in each expert's queue.
+__global__ void route_scan_kernel(int* __restrict__ ws, int* __restrict__ counts, int nblocks, int E, int k) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int running = 0;
+  for (int j = 0; j < k; ++j) {
+    for (int b = 0; b < nblocks; ++b) {
+      const long long o = (static_cast<long long>(b) * k + j) * E + e;
+      const int v = ws[o];
+      ws[o] = running;
+      running += v;
+    }
+  }
+  counts[e] = running;
+}
+
+__global__ void __launch_bounds__(kRouteBlock) route_rank_kernel(const int* __restrict__ idx,
+                                                                const int* __restrict__ ws, int* __restrict__ loc,
+                                                                int* __restrict__ slot_src, int S, int E, int k,
+                                                                int C) {
+  extern __shared__ int cnt[];
+  const int b = blockIdx.x;
+  const int s = b * kRouteBlock + threadIdx.x;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int j = 0; j < k; ++j) {
+    for (int e = threadIdx.x; e < E; e += kRouteBlock) cnt[e] = 0;
+    __syncthreads();
+    int e = -1;
+    if (s < S) {
+      e = idx[static_cast<long long>(j) * S + s];
+      if (e >= E) e = -1;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, e);
+    const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    for (int w = 0; w < kRouteBlock / 32; ++w) {
+      if (warp == w && e >= 0 && lane == leader) {
+        base = cnt[e];
+        cnt[e] = base + __popc(peers);
+      }
+      __syncthreads();
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (s < S) {
+      int l = kInvalidLoc;
+      if (e >= 0) {
+        l = ws[(static_cast<long long>(b) * k + j) * E + e] + base + rank_in_warp;
+        if (slot_src != nullptr && l < C) slot_src[static_cast<long long>(e) * C + l] = s * k + j;
+      }
+      loc[static_cast<long long>(j) * S + s] = l;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void slot_map_kernel(const int* __restrict__ idx, const int* __restrict__ loc, int* __restrict__ slot_src,
+                                int S, int E, int k, int C) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(S) * k) return;
+  const int j = static_cast<int>(i / S);
+  const int s = static_cast<int>(i - static_cast<long long>(j) * S);
+  const int e = idx[i];
+  const int l = loc[i];
+  if (e >= 0 && e < E && l >= 0 && l < C) slot_src[static_cast<long long>(e) * C + l] = s * k + j;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 16-byte vector helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct Vec;  // 16 bytes of T
+template <>
+struct Vec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void unpack(const uint4& u, float* f) {
+    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+  }
+};
+template <>
+struct Vec<__half> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void unpack(const uint4& u, float* f) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void unpack(const uint4& u, float* f) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ------------------------------------------------------------------------------------------------
+// encode: slot-centric row gather (+ optional remote push and release counters)
+// ------------------------------------------------------------------------------------------------
+constexpr int kEncThreads = 256;
+constexpr int kEncWarps = kEncThreads / 32;
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kEncThreads)
+encode_rows_kernel(const T* __restrict__ x, const float* __restrict__ gates, const int* __restrict__ slot_src,
+                   T* __restrict__ out, const unsigned long long* __restrict__ dst_ptr_table,
+                   const unsigned long long* __restrict__ signal_ptr_table, int chunk_rows, int S, int E, int k, int C,
+                   int M, int rot_chunks) {
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int chunks_per_expert = (C + chunk_rows - 1) / chunk_rows;
+  const long long total_chunks = static_cast<long long>(E) * chunks_per_expert;
+  for (long long ci = blockIdx.x; ci < total_chunks; ci += gridDim.x) {
+    const long long c = (ci + rot_chunks) % total_chunks;
+    const int e = static_cast<int>(c / chunks_per_expert);
+    const int r0 = static_cast<int>(c - static_cast<long long>(e) * chunks_per_expert) * chunk_rows;
+    const int r1 = min(r0 + chunk_rows, C);
+    T* dst_e = dst_ptr_table != nullptr ? reinterpret_cast<T*>(dst_ptr_table[e])
+                                        : out + static_cast<long long>(e) * C * M;
+    for (int r = r0 + warp; r < r1; r += kEncWarps) {
+      const int src = slot_src[static_cast<long long>(e) * C + r];
+      T* drow = dst_e + static_cast<long long>(r) * M;
+      if (src < 0) {
+        if constexpr (VEC) {
+          const uint4 z = make_uint4(0, 0, 0, 0);
+          for (int v = lane; v < M / Vec<T>::N; v += 32) ptx::st_na_v4(reinterpret_cast<uint4*>(drow) + v, z);
+        } else {
+          for (int m = lane; m < M; m += 32) drow[m] = from_f<T>(0.0f);
+        }
+        continue;
+      }
+      const int tok = src / k;
+      const int j = src - tok * k;
+      const float g = gates != nullptr ? gates[static_cast<long long>(j) * S + tok] : 1.0f;
+      const T* srow = x + static_cast<long long>(tok) * M;
+      if constexpr (VEC) {
+        const int nv = M / Vec<T>::N;
+        const uint4* sv = reinterpret_cast<const uint4*>(srow);
+        uint4* dv = reinterpret_cast<uint4*>(drow);
+        int v = lane;
+        for (; v + 96 < nv; v += 128) {
+          uint4 a[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) a[u] = ptx::ld_nc_v4(sv + v + 32 * u);
+          if (gates != nullptr) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float f[Vec<T>::N];
+              Vec<T>::unpack(a[u], f);
+#pragma unroll
+              for (int q = 0; q < Vec<T>::N; ++q) f[q] *= g;
+              a[u] = Vec<T>::pack(f);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) ptx::st_na_v4(dv + v + 32 * u, a[u]);
+        }
+        for (; v < nv; v += 32) {
+          uint4 a = ptx::ld_nc_v4(sv + v);
+          if (gates != nullptr) {
+            float f[Vec<T>::N];
+            Vec<T>::unpack(a, f);
+#pragma unroll
+            for (int q = 0; q < Vec<T>::N; ++q) f[q] *= g;
+            a = Vec<T>::pack(f);
+          }
+          ptx::st_na_v4(dv + v, a);
+        }
+      } else {
+        for (int m = lane; m < M; m += 32) drow[m] = from_f<T>(to_f<T>(srow[m]) * g);
+      }
+    }
+    if (signal_ptr_table != nullptr) {
+      __syncthreads();  // every warp's stores of this chunk are issued and ordered before the release below
+      if (threadIdx.x == 0) {
+        ptx::fence_acq_rel_sys();
+        ptx::red_add_release_sys(reinterpret_cast<uint32_t*>(signal_ptr_table[e]) + r0 / chunk_rows, 1u);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode: token-centric weighted gather of k rows
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxK = 16;
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256)
+decode_rows_kernel(const T* __restrict__ buf, const float* __restrict__ gates, const int* __restrict__ idx,
+                   const int* __restrict__ loc, T* __restrict__ out, const uint32_t* __restrict__ wait_flags,
+                   uint32_t wait_target, int S, int E, int k, int C, int M) {
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long long s = static_cast<long long>(blockIdx.x) * 8 + warp; s < S; s += static_cast<long long>(gridDim.x) * 8) {
+    const T* rows[kMaxK];
+    float w[kMaxK];
+    int nsel = 0;
+    for (int j = 0; j < k; ++j) {
+      const int e = idx[static_cast<long long>(j) * S + s];
+      const int l = loc[static_cast<long long>(j) * S + s];
+      if (e >= 0 && e < E && l >= 0 && l < C) {
+        if (wait_flags != nullptr) {
+          if (lane == 0) ptx::wait_flag_ge_sys(wait_flags + e, wait_target);
+          __syncwarp();
+        }
+        rows[nsel] = buf + (static_cast<long long>(e) * C + l) * M;
+        w[nsel] = gates != nullptr ? gates[static_cast<long long>(j) * S + s] : 1.0f;
+        ++nsel;
+      }
+    }
+    T* orow = out + s * M;
+    if constexpr (VEC) {
+      const int nv = M / Vec<T>::N;
+      for (int v0 = lane; v0 < nv; v0 += 64) {
+        float acc[2][Vec<T>::N];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int q = 0; q < Vec<T>::N; ++q) acc[u][q] = 0.0f;
+        for (int t = 0; t < nsel; ++t) {
+          uint4 a[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (v0 + 32 * u < nv) a[u] = ptx::ld_v4(reinterpret_cast<const uint4*>(rows[t]) + v0 + 32 * u);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (v0 + 32 * u < nv) {
+              float f[Vec<T>::N];
+              Vec<T>::unpack(a[u], f);
+#pragma unroll
+              for (int q = 0; q < Vec<T>::N; ++q) acc[u][q] = fmaf(w[t], f[q], acc[u][q]);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (v0 + 32 * u < nv) ptx::st_na_v4(reinterpret_cast<uint4*>(orow) + v0 + 32 * u, Vec<T>::pack(acc[u]));
+      }
+    } else {
+      for (int m = lane; m < M; m += 32) {
+        float acc = 0.0f;
+        for (int t = 0; t < nsel; ++t) acc = fmaf(w[t], to_f<T>(rows[t][m]), acc);
+        orow[m] = from_f<T>(acc);
+      }
+    }
+  }
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256)
+gate_grad_kernel(const T* __restrict__ a, const T* __restrict__ buf, const int* __restrict__ idx,
+                 const int* __restrict__ loc, float* __restrict__ dgate, int S, int E, int k, int C, int M) {
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long long s = static_cast<long long>(blockIdx.x) * 8 + warp; s < S; s += static_cast<long long>(gridDim.x) * 8) {
+    const T* arow = a + s * M;
+    for (int j = 0; j < k; ++j) {
+      const int e = idx[static_cast<long long>(j) * S + s];
+      const int l = loc[static_cast<long long>(j) * S + s];
+      float acc = 0.0f;
+      if (e >= 0 && e < E && l >= 0 && l < C) {
+        const T* brow = buf + (static_cast<long long>(e) * C + l) * M;
+        if constexpr (VEC) {
+          const int nv = M / Vec<T>::N;
+          for (int v = lane; v < nv; v += 32) {
+            float fa[Vec<T>::N], fb[Vec<T>::N];
+            Vec<T>::unpack(ptx::ld_v4(reinterpret_cast<const uint4*>(arow) + v), fa);
+            Vec<T>::unpack(ptx::ld_v4(reinterpret_cast<const uint4*>(brow) + v), fb);
+#pragma unroll
+            for (int q = 0; q < Vec<T>::N; ++q) acc = fmaf(fa[q], fb[q], acc);
+          }
+        } else {
+          for (int m = lane; m < M; m += 32) acc = fmaf(to_f<T>(arow[m]), to_f<T>(brow[m]), acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      }
+      if (lane == 0) dgate[static_cast<long long>(j) * S + s] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused gating forward: softmax + top-k + aux-loss partial sums, one warp per token
+// ------------------------------------------------------------------------------------------------
+template <int VPT>
+__global__ void __launch_bounds__(256)
+gate_topk_kernel(const float* __restrict__ logits, float* __restrict__ scores, int* __restrict__ idx,
+                 float* __restrict__ topk_scores, float* __restrict__ me_partial, int* __restrict__ ce_partial, int S,
+                 int E, int k, int tokens_per_block) {
+  __shared__ float sm_me[8][32 * VPT];
+  __shared__ int sm_ce[8][32 * VPT];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  float me[VPT];
+  int ce[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) { me[i] = 0.0f; ce[i] = 0; }
+  const long long s_begin = static_cast<long long>(blockIdx.x) * tokens_per_block;
+  const long long s_end = min(s_begin + tokens_per_block, static_cast<long long>(S));
+  for (long long s = s_begin + warp; s < s_end; s += 8) {
+    float v[VPT];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int e = lane + 32 * i;
+      v[i] = e < E ? logits[s * E + e] : -INFINITY;
+      mx = fmaxf(mx, v[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      v[i] = (lane + 32 * i < E) ? expf(v[i] - mx) : 0.0f;
+      sum += v[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int e = lane + 32 * i;
+      v[i] *= inv;
+      if (e < E) {
+        scores[s * E + e] = v[i];
+        me[i] += v[i];
+      }
+    }
+    // iterative arg-max, ties broken towards the lower expert id
+    unsigned taken = 0;  // bit i: this lane's i-th value already selected
+    for (int j = 0; j < k; ++j) {
+      float best = -1.0f;
+      int best_e = 0x7fffffff;
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        const int e = lane + 32 * i;
+        if (e < E && !((taken >> i) & 1u) && (v[i] > best)) { best = v[i]; best_e = e; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oe = __shfl_xor_sync(0xffffffffu, best_e, o);
+        if (ob > best || (ob == best && oe < best_e)) { best = ob; best_e = oe; }
+      }
+      if ((best_e & 31) == lane && best_e < E) {
+        taken |= 1u << (best_e >> 5);
+        if (j == 0) ce[best_e >> 5] += 1;
+      }
+      if (lane == 0) {
+        idx[static_cast<long long>(j) * S + s] = best_e;
+        topk_scores[static_cast<long long>(j) * S + s] = best;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) { sm_me[warp][lane + 32 * i] = me[i]; sm_ce[warp][lane + 32 * i] = ce[i]; }
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += 256) {
+    float a = 0.0f;
+    int c = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += sm_me[w][e]; c += sm_ce[w][e]; }
+    me_partial[static_cast<long long>(blockIdx.x) * E + e] = a;
+    ce_partial[static_cast<long long>(blockIdx.x) * E + e] = c;
+  }
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+}  // namespace
+
+size_t route_workspace_ints(int S, int E, int k) {
+  const size_t nblocks = (static_cast<size_t>(S) + kRouteBlock - 1) / kRouteBlock;
+  return (nblocks + 1) * static_cast<size_t>(k) * E;
+}
+
+cudaError_t route_locations(const int* idx, int* loc, int* counts, int* workspace, int S, int E, int k,
+                            cudaStream_t stream) {
+  if (S <= 0) return cudaMemsetAsync(counts, 0, sizeof(int) * E, stream);
+  const int nblocks = (S + kRouteBlock - 1) / kRouteBlock;
+  const size_t smem = sizeof(int) * E;
+  route_hist_kernel<<<nblocks, kRouteBlock, smem, stream>>>(idx, workspace, S, E, k);
+  route_scan_kernel<<<(E + 127) / 128, 128, 0, stream>>>(workspace, counts, nblocks, E, k);
+  route_rank_kernel<<<nblocks, kRouteBlock, smem, stream>>>(idx, workspace, loc, nullptr, S, E, k, 0);
+  return cudaGetLastError();
+}
+
+cudaError_t build_slot_map(const int* idx, const int* loc, int* slot_src, int S, int E, int k, int C,
+                           cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(slot_src, 0xFF, sizeof(int) * static_cast<size_t>(E) * C, stream);
+  if (e != cudaSuccess) return e;
+  const long long n = static_cast<long long>(S) * k;
+  if (n > 0) slot_map_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(idx, loc, slot_src, S, E, k, C);
+  return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t encode_rows_t(const void* x, const void* gates, const int* slot_src, void* out,
+                                 const unsigned long long* dst_ptr_table, const unsigned long long* signal_ptr_table,
+                                 int signal_rows, int S, int E, int k, int C, int M, int rot, cudaStream_t stream) {
+  if (E <= 0 || C <= 0 || M <= 0) return cudaSuccess;
+  const int chunk_rows = signal_rows > 0 ? signal_rows : 16;
+  const long long chunks = static_cast<long long>(E) * ((C + chunk_rows - 1) / chunk_rows);
+  const int grid = static_cast<int>(chunks < 4LL * num_sms() ? chunks : 4LL * num_sms());
+  const bool vec = (M % Vec<T>::N == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                   (dst_ptr_table != nullptr || (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (vec)
+    encode_rows_kernel<T, true><<<grid, kEncThreads, 0, stream>>>(
+        static_cast<const T*>(x), static_cast<const float*>(gates), slot_src, static_cast<T*>(out), dst_ptr_table,
+        signal_ptr_table, chunk_rows, S, E, k, C, M, rot);
+  else
+    encode_rows_kernel<T, false><<<grid, kEncThreads, 0, stream>>>(
+        static_cast<const T*>(x), static_cast<const float*>(gates), slot_src, static_cast<T*>(out), dst_ptr_table,
+        signal_ptr_table, chunk_rows, S, E, k, C, M, rot);
+  return cudaGetLastError();
+}
+
+cudaError_t encode_rows(const void* x, const void* gates, const int* slot_src, void* out,
+                        const unsigned long long* dst_ptr_table, const unsigned long long* signal_ptr_table,
+                        int signal_rows, int S, int E, int k, int C, int M, int elem_type, int row_begin, int row_end,
+                        cudaStream_t stream) {
+  (void)row_end;
+  switch (elem_type) {
+    case ET_F32: return encode_rows_t<float>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, signal_rows, S, E, k, C, M, row_begin, stream);
+    case ET_F16: return encode_rows_t<__half>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, signal_rows, S, E, k, C, M, row_begin, stream);
+    case ET_BF16: return encode_rows_t<__nv_bfloat16>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, signal_rows, S, E, k, C, M, row_begin, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <typename T>
+static cudaError_t decode_rows_t(const void* buf, const void* gates, const int* idx, const int* loc, void* out,
+                                 const uint32_t* wait_flags, uint32_t wait_target, int S, int E, int k, int C, int M,
+                                 cudaStream_t stream) {
+  if (S <= 0 || M <= 0) return cudaSuccess;
+  if (k > kMaxK) return cudaErrorInvalidValue;
+  const long long want = (static_cast<long long>(S) + 7) / 8;
+  const int grid = static_cast<int>(want < 8LL * num_sms() ? want : 8LL * num_sms());
+  const bool vec = (M % Vec<T>::N == 0) && ((reinterpret_cast<uintptr_t>(buf) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (vec)
+    decode_rows_kernel<T, true><<<grid, 256, 0, stream>>>(static_cast<const T*>(buf), static_cast<const float*>(gates),
+                                                          idx, loc, static_cast<T*>(out), wait_flags, wait_target, S,
+                                                          E, k, C, M);
+  else
+    decode_rows_kernel<T, false><<<grid, 256, 0, stream>>>(static_cast<const T*>(buf), static_cast<const float*>(gates),
+                                                           idx, loc, static_cast<T*>(out), wait_flags, wait_target, S,
+                                                           E, k, C, M);
+  return cudaGetLastError();
+}
+
+cudaError_t decode_rows(const void* buf, const void* gates, const int* idx, const int* loc, void* out,
+                        const uint32_t* wait_flags, uint32_t wait_target, int S, int E, int k, int C, int M,
+                        int elem_type, cudaStream_t stream) {
+  switch (elem_type) {
+    case ET_F32: return decode_rows_t<float>(buf, gates, idx, loc, out, wait_flags, wait_target, S, E, k, C, M, stream);
+    case ET_F16: return decode_rows_t<__half>(buf, gates, idx, loc, out, wait_flags, wait_target, S, E, k, C, M, stream);
+    case ET_BF16: return decode_rows_t<__nv_bfloat16>(buf, gates, idx, loc, out, wait_flags, wait_target, S, E, k, C, M, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <typename T>
+static cudaError_t gate_grad_t(const void* a, const void* buf, const int* idx, const int* loc, void* dgate, int S, int E,
+                               int k, int C, int M, cudaStream_t stream) {
+  if (S <= 0) return cudaSuccess;
+  const long long want = (static_cast<long long>(S) + 7) / 8;
+  const int grid = static_cast<int>(want < 8LL * num_sms() ? want : 8LL * num_sms());
+  const bool vec = (M % Vec<T>::N == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(buf) & 15) == 0);
+  if (vec)
+    gate_grad_kernel<T, true><<<grid, 256, 0, stream>>>(static_cast<const T*>(a), static_cast<const T*>(buf), idx, loc,
+                                                        static_cast<float*>(dgate), S, E, k, C, M);
+  else
+    gate_grad_kernel<T, false><<<grid, 256, 0, stream>>>(static_cast<const T*>(a), static_cast<const T*>(buf), idx, loc,
+                                                         static_cast<float*>(dgate), S, E, k, C, M);
+  return cudaGetLastError();
+}
+
+cudaError_t gate_grad(const void* a, const void* buf, const int* idx, const int* loc, void* dgate, int S, int E, int k,
+                      int C, int M, int elem_type, cudaStream_t stream) {
+  switch (elem_type) {
+    case ET_F32: return gate_grad_t<float>(a, buf, idx, loc, dgate, S, E, k, C, M, stream);
+    case ET_F16: return gate_grad_t<__half>(a, buf, idx, loc, dgate, S, E, k, C, M, stream);
+    case ET_BF16: return gate_grad_t<__nv_bfloat16>(a, buf, idx, loc, dgate, S, E, k, C, M, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t gate_topk_forward(const float* logits, float* scores, int* idx, float* topk_scores, float* me_partial,
+                              int* ce_partial, int S, int E, int k, cudaStream_t stream) {
+  if (S <= 0) return cudaSuccess;
+  const int tokens_per_block = 256;
+  const int grid = (S + tokens_per_block - 1) / tokens_per_block;
+#define TB_GATE(VPTv)                                                                                              \
+  gate_topk_kernel<VPTv><<<grid, 256, 0, stream>>>(logits, scores, idx, topk_scores, me_partial, ce_partial, S, E, k, \
+                                                   tokens_per_block)
+  if (E <= 32) TB_GATE(1);
+  else if (E <= 64) TB_GATE(2);
+  else if (E <= 128) TB_GATE(4);
+  else if (E <= 256) TB_GATE(8);
+  else if (E <= 512) TB_GATE(16);
+  else return cudaErrorInvalidValue;
+#undef TB_GATE
+  return cudaGetLastError();
+}
+
+}  // namespace tb

@@ -1,0 +1,38 @@
+// In-kernel peer-to-peer collectives over NVLink (p2p_kernels.cu).  All buffers live in the symmetric heap
+// (symm_heap.h): every rank holds the same offsets, `peer_table[r]` is rank r's heap base mapped in this process.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tb {
+
+constexpr int kMaxPeers = 16;
+
+struct PushPlan {
+  // For every destination peer p: copy `bytes[p]` bytes from local `src + src_off[p]` to
+  // peer_table[p] + dst_heap_off + dst_off[p].   All offsets/sizes are multiples of 16 bytes... or not:
+  // unaligned tails are handled with byte copies.
+  long long src_off[kMaxPeers];
+  long long dst_off[kMaxPeers];
+  long long bytes[kMaxPeers];
+};
+
+// Counters (uint32, inside the heap, zero-initialised, monotonically increasing):
+//   ready[W] at heap offset ready_off: ready[src] on rank d counts "d's receive region is free" credits that d
+//             granted to src.  done[W] at done_off: done[src] on rank d counts finished pushes of src into d.
+// `epoch` is the 1-based call number on this (ready, done) counter pair.
+cudaError_t p2p_push(const void* src, const PushPlan& plan, const unsigned long long* peer_table,
+                     long long dst_heap_off, long long ready_off, long long done_off, int rank, int world,
+                     uint32_t epoch, int blocks_per_peer, cudaStream_t stream);
+
+// out[i] = sum_p peer_p[stage_off + slice_off + i]  for i in [0, n)   (one-shot pull-reduce; fp32 accumulate).
+// Callers bracket it with p2p_barrier so that all stages are written / may be overwritten.
+cudaError_t p2p_reduce_slice(void* out, const unsigned long long* peer_table, long long stage_off,
+                             long long slice_off_bytes, long long n_elems, int elem_type, int rank, int world,
+                             bool is_max, cudaStream_t stream);
+
+// All ranks arrive and wait (system-scope release/acquire); `epoch` 1-based per counter array at bar_off (uint32[W]).
+cudaError_t p2p_barrier(const unsigned long long* peer_table, long long bar_off, int rank, int world, uint32_t epoch,
+                        cudaStream_t stream);
+
+}  // namespace tb

@@ -1,0 +1,158 @@
+#include "symm_heap.h"
+
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda_runtime.h>
+#include <torch/extension.h>
+
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+
+#include "moe_kernels.h"
+#include "p2p_kernels.h"
+
+namespace tb {
+
+#define TB_CUDA_OK(expr)                                                                              \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      throw std::runtime_error(std::string("tutel_b200 symm_heap: ") + cudaGetErrorString(_e) + " at " #expr); \
+  } while (0)
+
+SymmHeap::SymmHeap(size_t bytes, int device) : bytes_(bytes), device_(device) {
+  c10::cuda::CUDAGuard guard(device);
+  TB_CUDA_OK(cudaMalloc(&local_, bytes));
+  TB_CUDA_OK(cudaMemset(local_, 0, bytes));
+  TB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d_peer_table_), sizeof(unsigned long long) * kMaxPeers));
+  peer_base_.assign(1, local_);
+  unsigned long long self = reinterpret_cast<unsigned long long>(local_);
+  TB_CUDA_OK(cudaMemcpy(d_peer_table_, &self, sizeof(self), cudaMemcpyHostToDevice));
+  TB_CUDA_OK(cudaDeviceSynchronize());
+}
+
+SymmHeap::~SymmHeap() {
+  try { close(); } catch (...) {}
+}
+
+std::string SymmHeap::ipc_handle() const {
+  cudaIpcMemHandle_t h;
+  TB_CUDA_OK(cudaIpcGetMemHandle(&h, local_));
+  return std::string(reinterpret_cast<const char*>(&h), sizeof(h));
+}
+
+void SymmHeap::open_peers(int rank, const std::vector<std::string>& handles) {
+  c10::cuda::CUDAGuard guard(device_);
+  const int world = static_cast<int>(handles.size());
+  if (world > kMaxPeers) throw std::runtime_error("tutel_b200 symm_heap: more peers than kMaxPeers");
+  rank_ = rank;
+  peer_base_.assign(world, nullptr);
+  std::vector<unsigned long long> table(world, 0);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      peer_base_[r] = local_;
+    } else {
+      if (handles[r].size() != sizeof(cudaIpcMemHandle_t)) throw std::runtime_error("bad IPC handle size");
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, handles[r].data(), sizeof(h));
+      void* p = nullptr;
+      TB_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      peer_base_[r] = p;
+    }
+    table[r] = reinterpret_cast<unsigned long long>(peer_base_[r]);
+  }
+  TB_CUDA_OK(cudaMemcpy(d_peer_table_, table.data(), sizeof(unsigned long long) * world, cudaMemcpyHostToDevice));
+  TB_CUDA_OK(cudaDeviceSynchronize());
+}
+
+void SymmHeap::close() {
+  if (closed_) return;
+  closed_ = true;
+  for (size_t r = 0; r < peer_base_.size(); ++r)
+    if (static_cast<int>(r) != rank_ && peer_base_[r] != nullptr) cudaIpcCloseMemHandle(peer_base_[r]);
+  if (d_peer_table_) cudaFree(d_peer_table_);
+  if (local_) cudaFree(local_);
+  d_peer_table_ = nullptr;
+  local_ = nullptr;
+}
+
+}  // namespace tb
+
+namespace {
+
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+#define TB_CHECK_CUDA(expr)                                                                          \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    TORCH_CHECK(_e == cudaSuccess, "tutel_b200 CUDA error: ", cudaGetErrorString(_e), " at ", #expr); \
+  } while (0)
+
+int et_of(at::ScalarType t) {
+  switch (t) {
+    case at::kFloat: return tb::ET_F32;
+    case at::kHalf: return tb::ET_F16;
+    case at::kBFloat16: return tb::ET_BF16;
+    default: TORCH_CHECK(false, "unsupported dtype for P2P reduce: ", t);
+  }
+}
+
+}  // namespace
+
+void register_symm_bindings(pybind11::module& m) {
+  namespace py = pybind11;
+  py::class_<tb::SymmHeap, std::shared_ptr<tb::SymmHeap>>(m, "SymmHeap")
+      .def(py::init([](int64_t bytes, int64_t device) {
+        return std::make_shared<tb::SymmHeap>(static_cast<size_t>(bytes), static_cast<int>(device));
+      }))
+      .def("ipc_handle", [](const tb::SymmHeap& h) { return py::bytes(h.ipc_handle()); })
+      .def("open_peers",
+           [](tb::SymmHeap& h, int64_t rank, const std::vector<py::bytes>& handles) {
+             std::vector<std::string> hs;
+             for (const auto& b : handles) hs.emplace_back(static_cast<std::string>(b));
+             h.open_peers(static_cast<int>(rank), hs);
+           })
+      .def("close", &tb::SymmHeap::close)
+      .def("bytes", [](const tb::SymmHeap& h) { return static_cast<int64_t>(h.bytes()); })
+      .def("world", &tb::SymmHeap::world)
+      .def("rank", &tb::SymmHeap::rank)
+      .def("base_ptr", [](const tb::SymmHeap& h, int64_t r) { return reinterpret_cast<int64_t>(h.base(static_cast<int>(r))); })
+      .def("peer_table_ptr", [](const tb::SymmHeap& h) { return reinterpret_cast<int64_t>(h.device_peer_table()); })
+      // Non-owning tensor view of `rank`'s heap at byte offset `off` (keep the heap alive while it is used).
+      .def("tensor",
+           [](std::shared_ptr<tb::SymmHeap> h, int64_t rank, int64_t off, std::vector<int64_t> sizes,
+              at::ScalarType dtype, int64_t device) {
+             uint8_t* p = static_cast<uint8_t*>(h->base(static_cast<int>(rank))) + off;
+             auto opts = at::TensorOptions().dtype(dtype).device(at::kCUDA, static_cast<int>(device));
+             return at::from_blob(p, sizes, [h](void*) {}, opts);
+           });
+
+  // src: any local CUDA tensor (bytes view); per-peer byte offsets/sizes as python lists.
+  m.def("p2p_push", [](const at::Tensor& src, std::vector<int64_t> src_off, std::vector<int64_t> dst_off,
+                       std::vector<int64_t> nbytes, int64_t peer_table, int64_t dst_heap_off, int64_t ready_off,
+                       int64_t done_off, int64_t rank, int64_t world, int64_t epoch, int64_t blocks_per_peer) {
+    TORCH_CHECK(src.is_cuda() && src.is_contiguous());
+    TORCH_CHECK(world <= tb::kMaxPeers && (int64_t)src_off.size() == world && (int64_t)dst_off.size() == world &&
+                (int64_t)nbytes.size() == world);
+    const c10::cuda::CUDAGuard guard(src.device());
+    tb::PushPlan plan{};
+    for (int p = 0; p < world; ++p) { plan.src_off[p] = src_off[p]; plan.dst_off[p] = dst_off[p]; plan.bytes[p] = nbytes[p]; }
+    TB_CHECK_CUDA(tb::p2p_push(src.data_ptr(), plan, reinterpret_cast<const unsigned long long*>(peer_table),
+                               dst_heap_off, ready_off, done_off, static_cast<int>(rank), static_cast<int>(world),
+                               static_cast<uint32_t>(epoch), static_cast<int>(blocks_per_peer), cur_stream()));
+  });
+  m.def("p2p_reduce_slice", [](at::Tensor& out, int64_t peer_table, int64_t stage_off, int64_t slice_off_bytes,
+                               int64_t rank, int64_t world, bool is_max) {
+    TORCH_CHECK(out.is_cuda() && out.is_contiguous());
+    const c10::cuda::CUDAGuard guard(out.device());
+    TB_CHECK_CUDA(tb::p2p_reduce_slice(out.data_ptr(), reinterpret_cast<const unsigned long long*>(peer_table),
+                                       stage_off, slice_off_bytes, out.numel(), et_of(out.scalar_type()),
+                                       static_cast<int>(rank), static_cast<int>(world), is_max, cur_stream()));
+  });
+  m.def("p2p_barrier", [](int64_t peer_table, int64_t bar_off, int64_t rank, int64_t world, int64_t epoch) {
+    TB_CHECK_CUDA(tb::p2p_barrier(reinterpret_cast<const unsigned long long*>(peer_table), bar_off,
+                                  static_cast<int>(rank), static_cast<int>(world), static_cast<uint32_t>(epoch),
+                                  cur_stream()));
+  });
+}
