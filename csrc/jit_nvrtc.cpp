@@ -8,7 +8,6 @@
 
 #include <map>
 #include <mutex>
-#include <regex>
 #include <string>
 #include <vector>
 
@@ -75,16 +74,43 @@ std::mutex& reg_mutex() {
 }
 
 // `// [thread_extent] blockIdx.x = 512` style launch annotations, as in the reference's kernel strings.
+// (hand-rolled scanner: std::regex is avoided on purpose - it is fragile across libstdc++ ABIs)
+size_t skip_ws(const std::string& s, size_t p) {
+  while (p < s.size() && (s[p] == ' ' || s[p] == '\t' || s[p] == '\n' || s[p] == '\r')) ++p;
+  return p;
+}
+
 void parse_extents(JitKernel& k) {
-  std::regex re(R"(\[thread_extent\]\s*(blockIdx|threadIdx)\.([xyz])\s*=\s*(\d+))");
-  for (auto it = std::sregex_iterator(k.source.begin(), k.source.end(), re); it != std::sregex_iterator(); ++it) {
-    const int axis = (*it)[2].str()[0] - 'x';
-    const int v = std::stoi((*it)[3].str());
-    if ((*it)[1].str() == "blockIdx") k.grid[axis] = v; else k.block[axis] = v;
+  const std::string& s = k.source;
+  const std::string tag = "[thread_extent]";
+  for (size_t p = s.find(tag); p != std::string::npos; p = s.find(tag, p + 1)) {
+    size_t q = skip_ws(s, p + tag.size());
+    bool is_block;
+    if (s.compare(q, 9, "blockIdx.") == 0) { is_block = true; q += 9; }
+    else if (s.compare(q, 10, "threadIdx.") == 0) { is_block = false; q += 10; }
+    else continue;
+    if (q >= s.size() || s[q] < 'x' || s[q] > 'z') continue;
+    const int axis = s[q] - 'x';
+    q = skip_ws(s, q + 1);
+    if (q >= s.size() || s[q] != '=') continue;
+    q = skip_ws(s, q + 1);
+    int v = 0;
+    bool any = false;
+    while (q < s.size() && s[q] >= '0' && s[q] <= '9') { v = v * 10 + (s[q] - '0'); ++q; any = true; }
+    if (!any) continue;
+    if (is_block) k.grid[axis] = v; else k.block[axis] = v;
   }
-  std::smatch m;
-  std::regex ent(R"(__global__\s+(?:__launch_bounds__\s*\([^)]*\)\s*)?void\s+(\w+)\s*\()");
-  if (std::regex_search(k.source, m, ent)) k.entry = m[1].str();
+  // entry point: the identifier that precedes the first '(' after `__global__ ... void`
+  size_t g = s.find("__global__");
+  while (g != std::string::npos && k.entry.empty()) {
+    size_t v = s.find("void", g);
+    if (v == std::string::npos) break;
+    size_t q = skip_ws(s, v + 4);
+    size_t b = q;
+    while (q < s.size() && (isalnum(static_cast<unsigned char>(s[q])) || s[q] == '_')) ++q;
+    if (q > b && skip_ws(s, q) < s.size() && s[skip_ws(s, q)] == '(') k.entry = s.substr(b, q - b);
+    else g = s.find("__global__", g + 1);
+  }
   TORCH_CHECK(!k.entry.empty(), "tutel_b200.jit: no `__global__ void NAME(` entry point found in source");
 }
 

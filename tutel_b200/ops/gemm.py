@@ -1,0 +1,198 @@
+"""Grouped expert GEMMs on the hand-written tcgen05 kernel (csrc/gemm_sm100.cu) with autograd.
+
+The reference runs its experts through ``torch.matmul`` -> cuBLAS (tutel/experts/ffn.py:114-118) followed by separate
+bias / activation kernels.  Here forward, data-gradient and weight-gradient are all launches of one persistent
+tcgen05/TMEM/TMA kernel; bias, ReLU and the ReLU gradient mask are fused into its epilogue, operands are consumed in
+whatever major-ness they already have (no transposes are materialised).
+
+Shapes (G = groups / local experts):
+    ``x [G, T, K]``;  weights either ``[G, N, K]`` ("nk", like ``batched_fc1_w``) or ``[G, K, N]`` ("kn", like
+    ``batched_fc2_w``);  result ``[G, T, N]``.
+"""
+from __future__ import annotations
+
+from typing import Any, Optional
+
+import torch
+
+from . import backend
+
+EPI_NONE, EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_GELU, EPI_BIAS_SILU, EPI_RELU_BWD = 0, 1, 2, 3, 4, 5
+
+
+def _ok_stride(t: torch.Tensor) -> bool:
+    es = t.element_size()
+    return (t.stride(-1) == 1 and (t.stride(-2) * es) % 16 == 0 and (t.dim() < 3 or (t.stride(0) * es) % 16 == 0 or t.size(0) == 1)
+            and t.data_ptr() % 16 == 0)
+
+
+def _prep(t: torch.Tensor) -> torch.Tensor:
+    if t.dim() == 2:
+        t = t.unsqueeze(0)
+    return t if _ok_stride(t) else t.contiguous()
+
+
+def raw_gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, epilogue: int = EPI_NONE,
+             bias: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
+             row_counts: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+             out_dtype: Optional[torch.dtype] = None, alpha: float = 1.0, b_group_div: int = 1, cta_group: int = 0,
+             block_n: int = 0, d_ptr_table: int = 0, signal_ptr_table: int = 0, wait_flags: int = 0,
+             wait_rows_per_flag: int = 0, wait_flags_per_group: int = 0, wait_target: int = 0,
+             max_ctas: int = 0) -> torch.Tensor:
+    """D[g] = epilogue(A[g] @ B[g // b_group_div]).
+
+    ``a``: ``[G, M, K]`` (or ``[G, K, M]`` when ``a_mn``);  ``b``: ``[Gb, N, K]`` (or ``[Gb, K, N]`` when ``b_mn``).
+    """
+    C = backend.require_ext()
+    a, b = _prep(a), _prep(b)
+    G = a.size(0)
+    M = a.size(2) if a_mn else a.size(1)
+    N = b.size(2) if b_mn else b.size(1)
+    if out is None:
+        out = torch.empty([G, M, N], dtype=out_dtype or a.dtype, device=a.device)
+    d = out if out.dim() == 3 else out.unsqueeze(0)
+    if bias is not None:
+        bias = bias.reshape(b.size(0), N)
+        if bias.stride(-1) != 1 or bias.dtype != a.dtype:
+            bias = bias.to(a.dtype).contiguous()
+    if aux is not None:
+        aux = _prep(aux)
+    C.gemm(a, b, d, a_mn, b_mn, epilogue, bias, aux, row_counts, float(alpha), int(b_group_div), int(cta_group),
+           int(block_n), int(d_ptr_table), int(signal_ptr_table), int(wait_flags), int(wait_rows_per_flag),
+           int(wait_flags_per_group), int(wait_target), int(max_ctas))
+    return out
+
+
+def _aligned(*dims: int) -> bool:
+    return all(d % 8 == 0 for d in dims)
+
+
+def can_use_tcgen05(x: torch.Tensor, w: torch.Tensor) -> bool:
+    return (backend.use_tcgen05(x) and w.dtype == x.dtype and w.is_cuda and x.dim() == 3 and w.dim() == 3 and
+            _aligned(x.size(-1), w.size(-1), w.size(-2)))
+
+
+class GroupedLinear(torch.autograd.Function):
+    """y[g] = x[g] @ W[g]^T (+ b)  for ``w_layout == 'nk'``  or  x[g] @ W[g] (+ b)  for ``'kn'`` - all on tcgen05."""
+
+    @staticmethod
+    def forward(ctx: Any, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], w_layout: str,
+                row_counts: Optional[torch.Tensor]):
+        ctx.w_layout = w_layout
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, w)
+        ctx.row_counts = row_counts
+        return raw_gemm(x, w, b_mn=(w_layout == 'kn'), epilogue=EPI_BIAS if bias is not None else EPI_NONE, bias=bias,
+                        row_counts=row_counts)
+
+    @staticmethod
+    def backward(ctx: Any, dy: torch.Tensor):
+        x, w = ctx.saved_tensors
+        dy = dy if _ok_stride(dy) else dy.contiguous()
+        kn = ctx.w_layout == 'kn'
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # dx[T,K] = dy[T,N] @ W (nk: W is [N,K] i.e. "kn" for this product; kn: W is [K,N] i.e. "nk")
+            dx = raw_gemm(dy, w, b_mn=not kn, row_counts=ctx.row_counts)
+            if ctx.row_counts is not None:
+                dx = _zero_tail(dx, ctx.row_counts)
+        if ctx.needs_input_grad[1]:
+            if kn:   # dW[K,N] = x^T[K,T] @ dy[T,N]
+                dw = raw_gemm(x, dy, a_mn=True, b_mn=True)
+            else:    # dW[N,K] = dy^T[N,T] @ x[T,K]
+                dw = raw_gemm(dy, x, a_mn=True, b_mn=True)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(dim=1, dtype=torch.float32).to(dy.dtype)
+        return dx, dw, db, None, None
+
+
+def _zero_tail(t: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    rows = torch.arange(t.size(1), device=t.device).view(1, -1, 1)
+    return torch.where(rows < counts.view(-1, 1, 1), t, torch.zeros((), dtype=t.dtype, device=t.device))
+
+
+def grouped_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, w_layout: str = 'nk',
+                   row_counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Batched per-expert linear layer; falls back to ``torch.matmul`` for dtypes/devices the kernel does not cover."""
+    if can_use_tcgen05(x, w) and (bias is None or bias.numel() == w.size(0) * (w.size(1) if w_layout == 'nk' else w.size(2))):
+        b = None if bias is None else bias.reshape(w.size(0), -1)
+        return GroupedLinear.apply(x, w, b, w_layout, row_counts)
+    y = torch.matmul(x, w.transpose(1, 2) if w_layout == 'nk' else w)
+    if bias is not None:
+        y = y + bias.reshape(w.size(0), 1, -1)
+    return y
+
+
+class FusedReluFFN(torch.autograd.Function):
+    """y = relu(x @ W1^T + b1) @ W2 + b2 with 2 forward and 4 backward launches, nothing else.
+
+    ``w1 [G, H, M]`` (nk), ``w2 [G, H, Mout]`` (kn) - the reference's ``batched_fc1_w`` / ``batched_fc2_w`` layout.
+    Forward keeps only the post-ReLU activation; its sign doubles as the ReLU mask fused into the dgrad epilogue.
+    """
+
+    @staticmethod
+    def forward(ctx: Any, x, w1, b1, w2, b2, row_counts):
+        act = raw_gemm(x, w1, epilogue=EPI_BIAS_RELU, bias=b1, row_counts=row_counts)
+        y = raw_gemm(act, w2, b_mn=True, epilogue=EPI_BIAS if b2 is not None else EPI_NONE, bias=b2,
+                     row_counts=row_counts)
+        ctx.save_for_backward(x, w1, w2, act)
+        ctx.has_b1, ctx.has_b2 = b1 is not None, b2 is not None
+        ctx.row_counts = row_counts
+        return y
+
+    @staticmethod
+    def backward(ctx: Any, dy: torch.Tensor):
+        x, w1, w2, act = ctx.saved_tensors
+        rc = ctx.row_counts
+        dy = dy if _ok_stride(dy) else dy.contiguous()
+        if rc is not None:
+            dy = _zero_tail(dy, rc)
+        # dh[T,H] = (dy[T,Mout] @ W2^T) * (act > 0)           W2 [H,Mout] is "nk" for this product
+        dh = raw_gemm(dy, w2, epilogue=EPI_RELU_BWD, aux=act, row_counts=rc)
+        if rc is not None:
+            dh = _zero_tail(dh, rc)
+            act = _zero_tail(act, rc)
+        dw2 = raw_gemm(act, dy, a_mn=True, b_mn=True) if ctx.needs_input_grad[3] else None      # [H,Mout] = act^T @ dy
+        db2 = dy.sum(dim=1, dtype=torch.float32).to(dy.dtype) if ctx.has_b2 and ctx.needs_input_grad[4] else None
+        dx = raw_gemm(dh, w1, b_mn=True, row_counts=rc) if ctx.needs_input_grad[0] else None    # [T,M] = dh @ W1
+        if dx is not None and rc is not None:
+            dx = _zero_tail(dx, rc)
+        dw1 = raw_gemm(dh, x, a_mn=True, b_mn=True) if ctx.needs_input_grad[1] else None        # [H,M] = dh^T @ x
+        db1 = dh.sum(dim=1, dtype=torch.float32).to(dh.dtype) if ctx.has_b1 and ctx.needs_input_grad[2] else None
+        return dx, dw1, db1, dw2, db2, None
+
+
+def fused_relu_ffn(x, w1, b1, w2, b2, row_counts=None):
+    b1 = None if b1 is None else b1.reshape(w1.size(0), -1)
+    b2 = None if b2 is None else b2.reshape(w2.size(0), -1)
+    return FusedReluFFN.apply(x, w1, b1, w2, b2, row_counts)
+
+
+_PROBE = None
+
+
+def classify_activation(fn) -> Optional[str]:
+    """Recognise ReLU (also when wrapped in a lambda, as the reference examples do) by probing it once."""
+    global _PROBE
+    if fn is None or fn is torch.relu or fn is torch.nn.functional.relu or isinstance(fn, torch.nn.ReLU):
+        return 'relu'
+    if isinstance(fn, str):
+        return fn
+    cached = getattr(fn, '_tutel_b200_kind', None)
+    if cached is not None:
+        return cached or None
+    if _PROBE is None:
+        _PROBE = torch.linspace(-4.0, 4.0, 257)
+    kind = ''
+    try:
+        with torch.no_grad():
+            a, b = fn(_PROBE.clone()), fn(_PROBE.clone())
+        if isinstance(a, torch.Tensor) and a.shape == _PROBE.shape and torch.equal(a, b) and torch.equal(a, torch.relu(_PROBE)):
+            kind = 'relu'
+    except Exception:  # noqa
+        kind = ''
+    try:
+        fn._tutel_b200_kind = kind
+    except Exception:  # noqa
+        pass
+    return kind or None

@@ -1,0 +1,125 @@
+"""Top-k routing: expert ids, queue locations, gate values, capacity (``tutel.moe.top_k_routing``).
+
+Semantics follow tutel/impls/fast_dispatch.py:143-204 exactly (stable token order, j-th choices queue behind all
+(j-1)-th choices, drop rule ``location >= capacity``, capacity rules for positive / zero / negative factors and the
+alignment round-up), but the implementation is different: no one-hot masks and no per-choice cumsum - a fused
+histogram / scan / rank pass (csrc/moe_kernels.cu on CUDA, csrc/cpu_kernels.cpp on CPU) produces locations, the
+per-expert counts and (on CUDA) the inverse slot->token map used by the gather-style encode kernel.
+"""
+from __future__ import annotations
+
+import logging
+from typing import List, Optional
+
+import torch
+
+from ..models import losses
+from ..parallel.communicate import get_world_rank, simple_all_reduce
+from . import backend
+
+
+class CriticalData(tuple):
+    """``(num_global_experts, indices_s, locations_s, gates_s, capacity, dispatch_count)`` plus cached stacked views.
+
+    Behaves like the reference's plain tuple; the extra attributes let the kernels consume ``[k, S]`` tensors
+    without re-stacking: ``idx_ks``, ``loc_ks`` (int32), ``gates_ks`` (differentiable), ``slot_src`` (lazy).
+    """
+
+    def __new__(cls, E, idx_ks, loc_ks, gates_ks, capacity, counts):
+        k = idx_ks.size(0)
+        self = super().__new__(cls, (E, [idx_ks[j] for j in range(k)], [loc_ks[j] for j in range(k)],
+                                     [gates_ks[j] for j in range(k)], capacity, counts))
+        self.idx_ks, self.loc_ks, self.gates_ks = idx_ks, loc_ks, gates_ks
+        self._slot_src = None
+        return self
+
+    @property
+    def slot_src(self) -> torch.Tensor:
+        if self._slot_src is None:
+            self._slot_src = build_slot_map(self.idx_ks, self.loc_ks, self[0], self[4])
+        return self._slot_src
+
+
+def _locations(idx_ks: torch.Tensor, E: int):
+    """Stable queue positions for [k, S] expert ids -> (loc [k,S] int32, counts [E] int32)."""
+    k, S = idx_ks.shape
+    if idx_ks.is_cuda and backend.has_cuda_ext():
+        loc, counts = backend.require_ext().route_locations(idx_ks, E, 0)[:2]
+        return loc, counts
+    if not idx_ks.is_cuda and backend.has_ext():
+        loc, counts = backend.ext().cpu_route_locations(idx_ks.contiguous(), E)
+        return loc, counts
+    # pure-torch fallback: one-hot cumulative sums
+    flat = idx_ks.reshape(-1).to(torch.int64)
+    onehot = torch.zeros([k * S, E], dtype=torch.int32, device=idx_ks.device)
+    onehot.scatter_(1, flat.unsqueeze(1), 1)
+    pos = torch.cumsum(onehot, dim=0) - 1
+    loc = pos.gather(1, flat.unsqueeze(1)).view(k, S).to(torch.int32)
+    return loc, onehot.sum(0).to(torch.int32)
+
+
+def build_slot_map(idx_ks: torch.Tensor, loc_ks: torch.Tensor, E: int, C: int) -> torch.Tensor:
+    """int32 [E*C]: ``token * k + choice`` occupying each slot, -1 for padding."""
+    k, S = idx_ks.shape
+    if idx_ks.is_cuda and backend.has_cuda_ext():
+        return backend.require_ext().build_slot_map(idx_ks.contiguous(), loc_ks.contiguous(), E, C)
+    slot = torch.full([E * C], -1, dtype=torch.int32, device=idx_ks.device)
+    valid = (loc_ks < C) & (idx_ks >= 0)
+    tok = torch.arange(S, device=idx_ks.device, dtype=torch.int32).unsqueeze(0) * k + \
+        torch.arange(k, device=idx_ks.device, dtype=torch.int32).unsqueeze(1)
+    slot[(idx_ks.to(torch.int64) * C + loc_ks.to(torch.int64))[valid]] = tok[valid]
+    return slot
+
+
+def extract_critical(scores: torch.Tensor, top_k: int, loss_fn=losses.gshard_loss, capacity_factor: float = 1.0,
+                     batch_prioritized_routing: bool = False, normalize_gate: bool = True, alignment: int = 1,
+                     group=None, inequivalent_tokens: bool = False):
+    num_global_experts = int(scores.size(1))
+    top_k_original, top_k = top_k, min(top_k, num_global_experts)
+    topk_indices = torch.topk(scores, top_k, dim=1).indices                     # [S, k]
+    idx_ks = topk_indices.t().contiguous().to(torch.int32)                      # [k, S]
+    gates_ks = scores.gather(1, topk_indices).t()                               # [k, S], differentiable
+
+    l_loss = loss_fn(scores, topk_indices) if loss_fn is not None else None
+
+    if batch_prioritized_routing:
+        # tokens claim slots in order of decreasing confidence instead of batch order
+        order = (-scores.max(dim=1)[0]).argsort(dim=0)
+        loc_sorted, counts = _locations(idx_ks[:, order].contiguous(), num_global_experts)
+        loc_ks = torch.empty_like(loc_sorted)
+        loc_ks[:, order] = loc_sorted
+    else:
+        loc_ks, counts = _locations(idx_ks, num_global_experts)
+
+    if top_k > 1 and normalize_gate:
+        denom = torch.clamp(gates_ks.sum(dim=0, keepdim=True), min=torch.finfo(gates_ks.dtype).eps)
+        gates_ks = gates_ks / denom
+
+    if inequivalent_tokens:
+        num_samples = torch.tensor(scores.size(0), device=scores.device)
+        num_samples = int(simple_all_reduce(num_samples, group=group, op=torch.distributed.ReduceOp.MAX))
+    else:
+        num_samples = int(scores.size(0))
+
+    samples_per_expert = (num_samples + num_global_experts - 1) // num_global_experts
+    if capacity_factor > 0:
+        capacity = top_k * int(capacity_factor * samples_per_expert)
+    else:
+        capacity = counts.max()
+        capacity = int(simple_all_reduce(capacity, group=group, op=torch.distributed.ReduceOp.MAX))
+        if capacity_factor < 0:
+            capacity = min(capacity, top_k * int(-capacity_factor * samples_per_expert))
+
+    remainder = capacity % alignment
+    if remainder > 0:
+        capacity = capacity + alignment - remainder
+
+    if logging.getLogger().isEnabledFor(logging.INFO) and get_world_rank(group) == 0:
+        logging.info('Capacity = %s, real-time capacity-factor for top-%s = %s', capacity, top_k_original,
+                     capacity / max(top_k * samples_per_expert, 1))
+
+    return CriticalData(num_global_experts, idx_ks, loc_ks, gates_ks, capacity, counts), l_loss
+
+
+def get_dispatch_count(critical_data):
+    return critical_data[-1]

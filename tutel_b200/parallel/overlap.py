@@ -1,0 +1,122 @@
+"""All-to-all / expert-FFN micro-pipelining (``a2a_ffn_overlap_degree``).
+
+Reference: tutel/impls/overlap.py:8-67 + the stream/event autograd Functions of tutel/impls/communicate.py:257-397
++ the chunked NCCL all-to-alls of tutel/custom/custom_kernel.cpp:520-654.
+
+The capacity dimension is cut into ``d`` chunks; the exchange of chunk *i+1* runs while the experts process chunk
+*i*, in forward and - mirrored - in backward.  Two small autograd Functions express this without touching the
+expert code: ``_Begin`` starts an exchange asynchronously (backward: waits for the mirrored exchange),
+``_End`` waits for it (backward: starts the mirrored exchange).  Because autograd replays nodes in reverse creation
+order, issuing all ``_Begin`` nodes first makes the backward pass pipeline itself the same way.
+
+Results are bit-identical for every ``d`` (the experts are row-wise independent).  On the fused NVLink path
+(:mod:`tutel_b200.parallel.fused`) the same knob selects the granularity of the arrival flags instead.
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, List
+
+import torch
+import torch.distributed as dist
+
+from . import communicate as C
+
+MAX_OVERLAP_DEGREE = 32
+
+
+class _Pending:
+    """An in-flight exchange: the (not yet valid) output buffer and a callable that makes the current stream wait."""
+    __slots__ = ('out', 'wait')
+
+    def __init__(self):
+        self.out, self.wait = None, None
+
+
+_COMM_STREAMS = {}
+
+
+def _comm_stream(device) -> torch.cuda.Stream:
+    key = torch.device(device).index
+    if key not in _COMM_STREAMS:
+        _COMM_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COMM_STREAMS[key]
+
+
+def _start_exchange(packed: torch.Tensor, group, pending: _Pending) -> None:
+    """Start an all-to-all along dim 0 of ``packed`` without blocking the current stream."""
+    packed = packed.contiguous()
+    t = C._p2p(group, packed)
+    if t is not None:
+        cur = torch.cuda.current_stream()
+        side = _comm_stream(packed.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            out = t.all_to_all(packed, copy=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        packed.record_stream(side)
+        out.record_stream(cur)
+        pending.out, pending.wait = out, (lambda: torch.cuda.current_stream().wait_event(ev))
+    elif packed.is_cuda:
+        out = torch.empty_like(packed)
+        work = dist.all_to_all_single(out, packed, group=group, async_op=True)
+        pending.out, pending.wait = out, work.wait
+    else:
+        pending.out, pending.wait = C.simple_all_to_all(packed, group), (lambda: None)
+
+
+class _Begin(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx: Any, packed: torch.Tensor, group, fwd: _Pending, bwd: _Pending):
+        ctx.bwd = bwd
+        _start_exchange(packed, group, fwd)
+        return fwd.out
+
+    @staticmethod
+    def backward(ctx: Any, grad: torch.Tensor):
+        # the mirrored exchange was started by _End.backward; `grad` is its output buffer
+        ctx.bwd.wait()
+        return ctx.bwd.out, None, None, None
+
+
+class _End(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx: Any, raw: torch.Tensor, group, fwd: _Pending, bwd: _Pending):
+        ctx.group, ctx.bwd = group, bwd
+        fwd.wait()
+        return raw.view_as(raw)
+
+    @staticmethod
+    def backward(ctx: Any, grad: torch.Tensor):
+        _start_exchange(grad, ctx.group, ctx.bwd)
+        return ctx.bwd.out, None, None, None
+
+
+def _async_all_to_all(x: torch.Tensor, input_dim: int, output_dim: int, group) -> Callable[[], torch.Tensor]:
+    """Start ``all_to_all(x, input_dim, output_dim)``; the returned callable finishes it (autograd-aware)."""
+    world = C.get_world_size(group)
+    fwd, bwd = _Pending(), _Pending()
+    raw = _Begin.apply(C._a2a_pack(x, output_dim, world), group, fwd, bwd)
+    return lambda: C._a2a_unpack(_End.apply(raw, group, fwd, bwd), input_dim)
+
+
+def a2a_ffn_overlap_forward(input: torch.Tensor, expert_fn: Callable[[torch.Tensor], torch.Tensor],
+                            a2a_ffn_overlap_degree: int, use_2dh: bool, group) -> torch.Tensor:
+    """``all_to_all(1,0) -> experts -> all_to_all(0,1)`` on ``[E', C', M]`` pipelined over ``d`` capacity chunks."""
+    d = a2a_ffn_overlap_degree
+    assert d <= MAX_OVERLAP_DEGREE, 'Excepting a2a_ffn_overlap_degree (%d) <= %d.' % (d, MAX_OVERLAP_DEGREE)
+    assert input.shape[1] % d == 0, 'Excepting input.shape[1] (%d) be multiple of a2a_ffn_overlap_degree (%d).' % (input.shape[1], d)
+    if C.get_world_size(group) == 1:
+        return expert_fn(input)
+    chunks = input.split(input.shape[1] // d, dim=1)
+    if use_2dh:
+        # hierarchical exchange has no asynchronous form: keep the chunking (identical numerics), run in order
+        outs = [C.all_to_all(expert_fn(C.all_to_all(c, 1, 0, group=group, use_2dh=True)), 0, 1, group=group, use_2dh=True)
+                for c in chunks]
+        return torch.cat(outs, dim=1)
+    arrivals = [_async_all_to_all(c, 1, 0, group) for c in chunks]        # all dispatch exchanges are in flight
+    returns: List[Callable[[], torch.Tensor]] = []
+    for arrive in arrivals:
+        y = expert_fn(arrive())                                           # waits only for its own chunk
+        returns.append(_async_all_to_all(y, 0, 1, group))                 # combine exchange overlaps the next chunk
+    return torch.cat([r() for r in returns], dim=1)

@@ -1,0 +1,257 @@
+"""NVLink peer-to-peer transport: symmetric heap + in-kernel collectives.
+
+This is the B200-native counterpart of the reference's private NCCL communicators and grouped ``ncclSend/ncclRecv``
+all-to-alls (tutel/custom/custom_kernel.cpp:327-518).  Every rank owns an arena (``_C.SymmHeap``, CUDA IPC mapped into
+all peers on the node); collectives are single kernels that *store* into the destination GPU's arena over NVLink and
+publish completion with ``red.release.sys`` counters (csrc/p2p_kernels.cu).  ``torch.distributed`` is only used to
+exchange the IPC handles.
+
+Layout of the arena::
+
+    [0, 64 KiB)                       counters: 16 slots x 3 arrays (ready / done / barrier) + MoE layer counters
+    [64 KiB, 64 KiB + stage_bytes)    staging region shared by the generic collectives below
+    [.. , heap_bytes)                 bump-allocated persistent buffers (MoE dispatch / combine buffers)
+"""
+from __future__ import annotations
+
+import logging
+import os
+import socket
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from ..ops import backend
+
+_CTRL_BYTES = 64 << 10
+_TRANSPORTS: Dict[int, Optional['P2PTransport']] = {}
+_MAX_PEERS = 16
+
+
+def _group_key(group) -> int:
+    return 0 if group is None or group is dist.group.WORLD else id(group)
+
+
+def _env_mode() -> str:
+    return os.environ.get('TUTEL_B200_COMM', 'p2p').lower()
+
+
+def transport_for(group) -> Optional['P2PTransport']:
+    """Return the P2P transport of ``group`` (created collectively on first use) or None if NCCL must be used."""
+    key = _group_key(group)
+    if key in _TRANSPORTS:
+        return _TRANSPORTS[key]
+    t = None
+    try:
+        t = _create(group)
+    except Exception as ex:  # noqa
+        logging.warning('tutel_b200: P2P transport unavailable (%s); falling back to NCCL', ex)
+        t = None
+    _TRANSPORTS[key] = t
+    return t
+
+
+def _create(group) -> Optional['P2PTransport']:
+    if _env_mode() in ('nccl', 'off', '0') or not backend.has_cuda_ext():
+        return None
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    world = dist.get_world_size(group)
+    if world <= 1 or world > _MAX_PEERS:
+        return None
+    if not (group is None or group is dist.group.WORLD) and world != dist.get_world_size():
+        return None  # sub-groups keep using NCCL in this version
+    if dist.get_backend(group) != 'nccl':
+        return None
+    # single NVLink domain check: same host, distinct devices, peer access possible
+    me = (socket.gethostname(), torch.cuda.current_device())
+    everyone = [None] * world
+    dist.all_gather_object(everyone, me, group=group)
+    ok = len({h for h, _ in everyone}) == 1 and len({d for _, d in everyone}) == world
+    if ok:
+        cur = torch.cuda.current_device()
+        ok = all(d == cur or torch.cuda.can_device_access_peer(cur, d) for _, d in everyone)
+    flags = [None] * world
+    dist.all_gather_object(flags, bool(ok), group=group)
+    if not all(flags):
+        return None
+    return P2PTransport(group)
+
+
+class P2PTransport:
+    def __init__(self, group):
+        from .. import _C
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.device = torch.cuda.current_device()
+        heap_mb = int(os.environ.get('TUTEL_B200_HEAP_MB', 3072))
+        stage_mb = int(os.environ.get('TUTEL_B200_STAGE_MB', 1280))
+        self.heap_bytes = heap_mb << 20
+        self.stage_off = _CTRL_BYTES
+        self.stage_bytes = min(stage_mb << 20, self.heap_bytes // 2)
+        self._bump = self.stage_off + self.stage_bytes
+        self.heap = _C.SymmHeap(self.heap_bytes, self.device)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.heap.ipc_handle(), group=group)
+        self.heap.open_peers(self.rank, handles)
+        dist.barrier(group=group)
+        self.peer_table = self.heap.peer_table_ptr()
+        self._C = _C
+        # counter slots: slot s -> ready at 256*s, done at 256*s+64, barrier at 256*s+128 (uint32[16] each)
+        self._epochs: Dict[int, int] = {}
+        self._named: Dict[str, tuple] = {}
+        self._next_slot = 2  # slot 0: generic push, slot 1: generic barrier/reduce
+
+    # ---- arena management -------------------------------------------------------------------------------------
+    def alloc(self, name: str, nbytes: int, align: int = 1024) -> int:
+        """Persistent, collectively-called allocation; the same name returns the same offset (size may not grow)."""
+        if name in self._named:
+            off, size = self._named[name]
+            if nbytes <= size:
+                return off
+            raise RuntimeError('tutel_b200 symmetric buffer %s cannot grow from %d to %d bytes' % (name, size, nbytes))
+        off = (self._bump + align - 1) // align * align
+        if off + nbytes > self.heap_bytes:
+            raise RuntimeError('tutel_b200 symmetric heap exhausted (%d MiB); raise TUTEL_B200_HEAP_MB' % (self.heap_bytes >> 20))
+        self._bump = off + nbytes
+        self._named[name] = (off, nbytes)
+        return off
+
+    def can_alloc(self, nbytes: int, align: int = 1024) -> bool:
+        return (self._bump + align - 1) // align * align + nbytes <= self.heap_bytes
+
+    def new_counter_slot(self) -> int:
+        s = self._next_slot
+        self._next_slot += 1
+        if 256 * (s + 1) > 16 << 10:
+            raise RuntimeError('tutel_b200: out of counter slots')
+        return s
+
+    def ctrl_alloc(self, name: str, nbytes: int) -> int:
+        """Zero-initialised counter storage inside the control page area [16 KiB, 64 KiB)."""
+        key = '__ctrl__' + name
+        if key in self._named:
+            return self._named[key][0]
+        cur = getattr(self, '_ctrl_bump', 16 << 10)
+        off = (cur + 127) // 128 * 128
+        if off + nbytes > _CTRL_BYTES:
+            raise RuntimeError('tutel_b200: control area exhausted')
+        self._ctrl_bump = off + nbytes
+        self._named[key] = (off, nbytes)
+        return off
+
+    def view(self, off: int, shape: Sequence[int], dtype: torch.dtype, rank: Optional[int] = None) -> torch.Tensor:
+        r = self.rank if rank is None else rank
+        return self.heap.tensor(r, off, list(shape), dtype, self.device)
+
+    def base_ptr(self, rank: int) -> int:
+        return self.heap.base_ptr(rank)
+
+    def _next_epoch(self, slot: int) -> int:
+        e = self._epochs.get(slot, 0) + 1
+        self._epochs[slot] = e
+        return e
+
+    # ---- primitives -----------------------------------------------------------------------------------------
+    def barrier(self, slot: int = 1) -> None:
+        self._C.p2p_barrier(self.peer_table, 256 * slot + 128, self.rank, self.world, self._next_epoch(('b', slot)))
+
+    def _blocks_per_peer(self, max_bytes: int) -> int:
+        if max_bytes <= (64 << 10):
+            return 1
+        if max_bytes <= (1 << 20):
+            return 4
+        return max(1, min(32, 296 // self.world))
+
+    def push(self, src: torch.Tensor, src_off: List[int], dst_off: List[int], nbytes: List[int], dst_heap_off: int,
+             slot: int = 0) -> None:
+        self._C.p2p_push(src, src_off, dst_off, nbytes, self.peer_table, dst_heap_off, 256 * slot, 256 * slot + 64,
+                         self.rank, self.world, self._next_epoch(slot), self._blocks_per_peer(max(nbytes)))
+
+    # ---- generic collectives (staging region; results are copied out so that callers may keep them) -------------
+    def fits(self, nbytes: int) -> bool:
+        return nbytes <= self.stage_bytes
+
+    def all_to_all(self, x: torch.Tensor, copy: bool = True) -> torch.Tensor:
+        nbytes = x.numel() * x.element_size()
+        if not self.fits(nbytes) or nbytes % self.world:
+            out = torch.empty_like(x)
+            dist.all_to_all_single(out, x, group=self.group)
+            return out
+        chunk = nbytes // self.world
+        self.push(x, [p * chunk for p in range(self.world)], [self.rank * chunk] * self.world, [chunk] * self.world,
+                  self.stage_off)
+        out = self.view(self.stage_off, x.shape, x.dtype)
+        return out.clone() if copy else out
+
+    def all_gather(self, x: torch.Tensor) -> torch.Tensor:
+        nbytes = x.numel() * x.element_size()
+        if not self.fits(nbytes * self.world):
+            out = torch.empty([self.world * x.numel()], device=x.device, dtype=x.dtype)
+            dist.all_gather_into_tensor(out, x.view(-1), group=self.group)
+            return out
+        self.push(x, [0] * self.world, [self.rank * nbytes] * self.world, [nbytes] * self.world, self.stage_off)
+        return self.view(self.stage_off, [self.world * x.numel()], x.dtype).clone()
+
+    def all_gather_v(self, x: torch.Tensor, sizes: List[int]) -> torch.Tensor:
+        es = x.element_size()
+        total = sum(sizes) * es
+        if not self.fits(total):
+            pieces = [torch.empty([n], dtype=x.dtype, device=x.device) for n in sizes]
+            dist.all_gather(pieces, x, group=self.group)
+            return torch.cat(pieces)
+        my_off = sum(sizes[: self.rank]) * es
+        n = sizes[self.rank] * es
+        self.push(x, [0] * self.world, [my_off] * self.world, [n] * self.world, self.stage_off)
+        return self.view(self.stage_off, [sum(sizes)], x.dtype).clone()
+
+    def all_to_all_v(self, x: torch.Tensor, matrix: List[List[int]]) -> torch.Tensor:
+        """``matrix[s][d]`` = elements rank s sends to rank d (known to every rank)."""
+        es = x.element_size()
+        in_list = matrix[self.rank]
+        out_list = [matrix[s][self.rank] for s in range(self.world)]
+        worst = max(sum(matrix[s][d] for s in range(self.world)) for d in range(self.world)) * es
+        if not self.fits(worst):
+            out = torch.empty([sum(out_list)], dtype=x.dtype, device=x.device)
+            dist.all_to_all_single(out, x[: sum(in_list)], output_split_sizes=out_list, input_split_sizes=in_list,
+                                   group=self.group)
+            return out
+        src_off, acc = [], 0
+        for n in in_list:
+            src_off.append(acc * es)
+            acc += n
+        dst_off = [sum(matrix[s][d] for s in range(self.rank)) * es for d in range(self.world)]
+        self.push(x, src_off, dst_off, [n * es for n in in_list], self.stage_off)
+        return self.view(self.stage_off, [sum(out_list)], x.dtype).clone()
+
+    # ---- reductions: one-shot pull over NVLink for small tensors --------------------------------------------------
+    _REDUCE_MAX_BYTES = 4 << 20
+
+    def supports_reduce(self, x: torch.Tensor, op) -> bool:
+        return (x.dtype in (torch.float32, torch.float16, torch.bfloat16) and op in (dist.ReduceOp.SUM, dist.ReduceOp.MAX)
+                and x.numel() * x.element_size() <= self._REDUCE_MAX_BYTES and x.numel() > 0)
+
+    def _stage(self, x: torch.Tensor) -> None:
+        self.view(self.stage_off, [x.numel()], x.dtype).copy_(x.reshape(-1))
+
+    def all_reduce_(self, x: torch.Tensor, op=dist.ReduceOp.SUM) -> torch.Tensor:
+        self._stage(x)
+        self.barrier()
+        out = x if x.is_contiguous() else torch.empty_like(x, memory_format=torch.contiguous_format)
+        self._C.p2p_reduce_slice(out, self.peer_table, self.stage_off, 0, self.rank, self.world, op == dist.ReduceOp.MAX)
+        self.barrier()
+        if out is not x:
+            x.copy_(out)
+        return x
+
+    def reduce_scatter(self, x: torch.Tensor, op=dist.ReduceOp.SUM) -> torch.Tensor:
+        self._stage(x)
+        self.barrier()
+        n = x.numel() // self.world
+        out = torch.empty_like(x[: x.size(0) // self.world])
+        self._C.p2p_reduce_slice(out, self.peer_table, self.stage_off, self.rank * n * x.element_size(), self.rank,
+                                 self.world, op == dist.ReduceOp.MAX)
+        self.barrier()
+        return out
