@@ -1,0 +1,196 @@
+#!/usr/bin/env python3
+"""Flagship benchmark: MoE-layer training step (fwd + bwd + SGD) throughput, whole job, device-timed.
+
+Config (BASELINE.json #2, weak scaling): helloworld model, top-2, 8 global experts (8/N per GPU), bf16,
+model_dim 4096, hidden 14336, 16 x 512 = 8192 tokens per GPU, capacity_factor 1.0, synthetic data, random init.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 \
+        bench.py --gpus 8 --steps 20 --warmup 5
+    python bench.py --impl reference ...      # the UNMODIFIED reference from baseline/_ref, same metric / config
+
+Prints one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+MODEL_DIM, HIDDEN, GLOBAL_EXPERTS, TOP_K = 4096, 14336, 8, 2
+BATCH, TOKENS = 16, 512
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', type=str, default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--model_dim', type=int, default=MODEL_DIM)
+    ap.add_argument('--hidden', type=int, default=HIDDEN)
+    ap.add_argument('--experts', type=int, default=GLOBAL_EXPERTS)
+    ap.add_argument('--top', type=int, default=TOP_K)
+    ap.add_argument('--overlap', type=int, default=1)
+    ap.add_argument('--no_e2e', action='store_true')
+    return ap.parse_args()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        ref = os.path.join(ROOT, 'baseline', '_ref')
+        if not os.path.isdir(os.path.join(ref, 'tutel')):
+            print(json.dumps({'impl': 'reference', 'unavailable': 'baseline/_ref is not installed (pip install --target baseline/_ref /root/reference)'}))
+            return
+        sys.path.insert(0, ref)
+        try:
+            from tutel import moe as moe_api, net as net_api, system as system_api  # noqa
+        except Exception as ex:  # noqa
+            print(json.dumps({'impl': 'reference', 'unavailable': 'import failed: %r' % (ex,)}))
+            return
+    else:
+        sys.path.insert(0, ROOT)
+        from tutel_b200 import moe as moe_api, net as net_api, system as system_api  # noqa
+
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    assert world == args.gpus or world == 1 and args.gpus == 1, 'launch with torchrun --nproc-per-node %d' % args.gpus
+    env = system_api.init_data_model_parallel(backend='nccl')
+    rank, device = env.global_rank, env.local_device
+    torch.cuda.set_device(device)
+    torch.set_default_dtype(torch.bfloat16)
+
+    assert args.experts % world == 0, 'global experts must divide over the GPUs'
+    local_experts = args.experts // world
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self._moe_layer = moe_api.moe_layer(
+                gate_type={'type': 'top', 'k': args.top, 'fp32_gate': False, 'capacity_factor': 1.0},
+                experts={'type': 'ffn', 'num_experts_per_device': local_experts, 'hidden_size_per_expert': args.hidden,
+                         'activation_fn': lambda x: F.relu(x)},
+                model_dim=args.model_dim,
+                scan_expert_func=lambda name, param: setattr(param, 'skip_allreduce', True),
+                seeds=(1, rank + 1, 1),
+                a2a_ffn_overlap_degree=args.overlap,
+            )
+
+        def forward(self, x):
+            return F.log_softmax(torch.sum(self._moe_layer(x), dim=2), dim=1)
+
+    model = Model().to(device)
+    optimizer = torch.optim.SGD(model.parameters(), lr=1e-5)
+    shared = [p for p in model.parameters() if not hasattr(p, 'skip_allreduce') and p.requires_grad]
+
+    torch.manual_seed(rank)
+    x_host = torch.randn([BATCH, TOKENS, args.model_dim], dtype=torch.float32).to(torch.bfloat16).pin_memory()
+    y_host = torch.zeros(BATCH, dtype=torch.int64).pin_memory()
+    x_dev, y_dev = x_host.to(device), y_host.to(device)
+
+    def step(x, y):
+        optimizer.zero_grad()
+        loss = F.nll_loss(model(x), y)
+        loss.backward()
+        if world > 1:
+            for p in shared:
+                p.grad /= world
+                p.grad = net_api.simple_all_reduce(p.grad)
+        optimizer.step()
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxreduce(v):
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    launches0 = 0
+    if args.impl == 'ours':
+        from tutel_b200.ops import backend
+    # ---------------- kernel-side number: inputs resident on the device ----------------
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev, y_dev)
+    sampler = None
+    if rank == 0:
+        sys.path.insert(0, ROOT)
+        try:
+            from tutel_b200.utils.timers import ClockSampler
+            sampler = ClockSampler(device.index or 0).start()
+        except Exception:  # noqa
+            sampler = None
+    sync()
+    if args.impl == 'ours':
+        launches0 = backend.launch_count()
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(x_dev, y_dev)
+    e1.record()
+    sync()
+    t_wall1 = time.time()
+    ms = maxreduce(e0.elapsed_time(e1))
+    launches = (backend.launch_count() - launches0) if args.impl == 'ours' else None
+    clocks = None
+    if sampler is not None:
+        sampler.stop()
+        clocks = sampler.summary(t_wall0, t_wall1)
+
+    # ---------------- end-to-end number: H2D of the step's inputs from pinned memory + D2H of the loss ----------------
+    e2e = None
+    if not args.no_e2e:
+        xb, yb = torch.empty_like(x_dev), torch.empty_like(y_dev)
+        for _ in range(2):
+            xb.copy_(x_host, non_blocking=True); yb.copy_(y_host, non_blocking=True)
+            float(step(xb, yb).item())
+        sync()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            xb.copy_(x_host, non_blocking=True)
+            yb.copy_(y_host, non_blocking=True)
+            last = float(step(xb, yb).item())          # device -> host read of the step's result
+        f1.record()
+        sync()
+        ms_e2e = maxreduce(f0.elapsed_time(f1))
+        e2e = {'value': world * BATCH * TOKENS * args.steps / (ms_e2e * 1e-3), 'unit': 'tokens/s',
+               'h2d_bytes_per_step': x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size(),
+               'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps, 'last_loss': last}
+
+    tokens = world * BATCH * TOKENS * args.steps
+    value = tokens / (ms * 1e-3)
+    flops = 4.0 * 3 * BATCH * TOKENS * args.model_dim * args.hidden * min(args.top, args.experts)  # per GPU per step
+    out = {
+        'metric': 'moe_layer_fwd_bwd_tokens_per_sec', 'value': value, 'unit': 'tokens/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic (random tokens, random-init weights)',
+        'impl': args.impl,
+        'config': {'model': 'helloworld moe_layer top-%d %d-expert ffn(relu) model_dim=%d hidden=%d' % (args.top, args.experts, args.model_dim, args.hidden),
+                   'global_batch': world * BATCH, 'seq_len': TOKENS, 'tokens_per_gpu': BATCH * TOKENS,
+                   'parallelism': 'ep%d (%d local experts/GPU)' % (world, local_experts), 'capacity_factor': 1.0,
+                   'step': 'zero_grad + fwd + nll_loss + bwd + gate-grad all-reduce + SGD',
+                   'l2': 'working set (weights %.1f GB + activations) exceeds the 126 MB L2; no explicit flush' % (
+                       local_experts * 2 * args.model_dim * args.hidden * 2 / 1e9),
+                   'a2a_ffn_overlap_degree': args.overlap},
+        'tflops_per_gpu': flops / (ms / args.steps * 1e-3) * 1e-12,
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'loss': float(loss.item()),
+    }
+    if rank == 0:
+        print(json.dumps(out))
+    sys.stdout.flush()
+
+
+if __name__ == '__main__':
+    main()

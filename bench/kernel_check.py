@@ -247,7 +247,8 @@ def run_jit(c):
     x = torch.randn(100000, device='cuda')
     y = torch.empty_like(x)
     _C.jit_invoke([x, y], [x.numel(), 3], [], h)
-    return dict(ok=bool(torch.allclose(y, x * 3 + 1)))
+    torch.cuda.synchronize()
+    return dict(ok=bool(torch.allclose(y, x * 3 + 1)), y=y[:4].tolist(), x=x[:4].tolist())
 
 
 RUNNERS = dict(gemm=run_gemm, route=run_route, dispatch=run_dispatch, gate=run_gate, jit=run_jit)

@@ -140,7 +140,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   using C = Cfg<CG, BN>;
   extern __shared__ uint8_t smem_raw[];
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // warp-uniform role id
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
   const bool is_leader = (cta_rank == 0);
@@ -177,10 +177,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);  // keep it in a uniform register
 
-  const int num_kb = (args.K * args.elt_bytes + kSwizzleBytes - 1) / kSwizzleBytes;
-  const int bk_elems = kSwizzleBytes / args.elt_bytes;       // K elements per stage
+  constexpr int kEltBytes = 2;                               // fp16 / bf16 operands (kind::f16)
+  const int num_kb = (args.K * kEltBytes + kSwizzleBytes - 1) / kSwizzleBytes;
+  constexpr int bk_elems = kSwizzleBytes / kEltBytes;        // K elements per stage
   const long long tile_step = gridDim.x / CG;
   const long long tile_first = blockIdx.x / CG;
   constexpr int kBand = (CG == 2) ? 8 : 16;
@@ -222,7 +223,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if constexpr (CG == 1) ptx::tma_load_3d(smem_a(s), &tmA, fb, k0, m0, tc.g);
             else ptx::tma_load_3d_2sm(smem_a(s), &tmA, fb, k0, m0, tc.g);
           } else {
-            const int chunk_elems = kSwizzleBytes / args.elt_bytes;
+            constexpr int chunk_elems = kSwizzleBytes / kEltBytes;
             const int chunk_bytes = bk_elems * kSwizzleBytes;
             const int nchunk = C::BM_CTA / chunk_elems;
             for (int c = 0; c < nchunk; ++c) {
@@ -237,7 +238,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if constexpr (CG == 1) ptx::tma_load_3d(smem_b(s), &tmB, fb, k0, n0, gb);
             else ptx::tma_load_3d_2sm(smem_b(s), &tmB, fb, k0, n0, gb);
           } else {
-            const int chunk_elems = kSwizzleBytes / args.elt_bytes;
+            constexpr int chunk_elems = kSwizzleBytes / kEltBytes;
             const int chunk_bytes = bk_elems * kSwizzleBytes;
             const int nchunk = C::BN_CTA / chunk_elems;
             for (int c = 0; c < nchunk; ++c) {
@@ -254,18 +255,25 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
+    // The whole warp walks the pipeline (keeps control flow convergent, descriptors in uniform registers);
+    // one elected lane issues the tcgen05 instructions.
     if (CG == 1 || is_leader) {
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
-      // Per-16/32-element K step inside one 128-byte swizzle row: +32 B (K-major) or +UMMA_K rows (MN-major).
-      const uint32_t mn_kstep_bytes = (32u / args.elt_bytes) * kSwizzleBytes;  // UMMA_K rows * 128 B
-      const uint32_t mn_chunk_bytes = static_cast<uint32_t>(bk_elems) * kSwizzleBytes;
-      const uint32_t a_lbo = A_MN ? mn_chunk_bytes : 16u;
-      const uint32_t b_lbo = B_MN ? mn_chunk_bytes : 16u;
-      const uint32_t a_kstep = A_MN ? mn_kstep_bytes : 32u;
-      const uint32_t b_kstep = B_MN ? mn_kstep_bytes : 32u;
+      // Descriptor = constant high word + low word {start>>4, lbo>>4}.  Advancing along K inside a stage and
+      // from stage to stage only adds to the 14-bit start-address field (smem < 256 KB, so it never carries).
+      constexpr uint32_t kMnChunkBytes = 64u * kSwizzleBytes;           // BK rows * 128 B (16-bit operands)
+      constexpr uint32_t kMnKStep = 16u * kSwizzleBytes;                // UMMA_K rows * 128 B
+      constexpr uint32_t a_lbo = A_MN ? kMnChunkBytes : 16u;
+      constexpr uint32_t b_lbo = B_MN ? kMnChunkBytes : 16u;
+      constexpr uint32_t a_kstep = (A_MN ? kMnKStep : 32u) >> 4;
+      constexpr uint32_t b_kstep = (B_MN ? kMnKStep : 32u) >> 4;
+      constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO | version 1 | SWIZZLE_128B
+      const uint32_t a_lo0 = ((smem_a(0) >> 4) & 0x3FFFu) | ((a_lbo >> 4) << 16);
+      const uint32_t b_lo0 = ((smem_b(0) >> 4) & 0x3FFFu) | ((b_lbo >> 4) << 16);
+      const uint32_t idesc = args.idesc;
       for (long long t = tile_first; t < args.num_tiles; t += tile_step) {
         const TileCoord tc = decode_tile<kBand>(t, args.tiles_m, args.tiles_n);
         if (args.row_counts != nullptr && tc.m_blk * C::BM >= args.row_counts[tc.g]) continue;
@@ -275,13 +283,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(full_bar(s), ph);
           ptx::tc_fence_after();
-          if (lane == 0) {
+          const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(s) * (C::STAGE_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(s) * (C::STAGE_BYTES >> 4);
+          if (ptx::elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = ptx::make_smem_desc_sw128(smem_a(s) + k * a_kstep, a_lbo, 1024u);
-              const uint64_t bd = ptx::make_smem_desc_sw128(smem_b(s) + k * b_kstep, b_lbo, 1024u);
-              if (args.elt_bytes == 2) ptx::umma_f16<CG>(d_tmem, ad, bd, args.idesc, (kb | k) != 0);
-              else ptx::umma_f8<CG>(d_tmem, ad, bd, args.idesc, (kb | k) != 0);
+              const uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + k * a_kstep);
+              const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + k * b_kstep);
+              ptx::umma_f16<CG>(d_tmem, ad, bd, idesc, (kb | k) != 0);
             }
             ptx::umma_commit<CG>(empty_bar(s));                       // smem slot reusable once these retire
             if (kb == num_kb - 1) ptx::umma_commit<CG>(tfull_bar(acc));  // accumulator complete
@@ -367,9 +376,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   f[0] = b0.x; f[1] = b0.y; f[2] = b0.z; f[3] = b0.w;
                   f[4] = b1.x; f[5] = b1.y; f[6] = b1.z; f[7] = b1.w;
                 } else {
-                  unpack8(*reinterpret_cast<const uint4*>(bias_g + (n + q * 8) * 2), args.elt_bytes == 2
-                              ? ((args.idesc >> 7) & 7u) == 1u
-                              : out_bf16, f);
+                  unpack8(*reinterpret_cast<const uint4*>(bias_g + (n + q * 8) * 2), ((args.idesc >> 7) & 7u) == 1u, f);
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];

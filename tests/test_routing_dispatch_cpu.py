@@ -1,0 +1,146 @@
+"""Per-op unit tests against dense oracles (the reference has none of these - SURVEY.md section 4)."""
+import pytest
+import torch
+
+from tutel_b200 import moe
+from tutel_b200.ops import routing, dispatch
+
+
+def _dense_locations(idx_ks, E):
+    """Oracle: one-hot cumsum exactly as tutel/impls/fast_dispatch.py:155-171."""
+    k, S = idx_ks.shape
+    locs, acc = [], torch.zeros(E, dtype=torch.int64)
+    for j in range(k):
+        mask = torch.nn.functional.one_hot(idx_ks[j].long(), E)
+        pos = torch.cumsum(mask, 0) - 1 + acc
+        locs.append((pos * mask).sum(1))
+        acc = acc + mask.sum(0)
+    return torch.stack(locs).to(torch.int32), acc.to(torch.int32)
+
+
+@pytest.mark.parametrize('S,E,k', [(10, 4, 2), (257, 7, 3), (64, 1, 1), (5, 8, 8)])
+def test_locations_match_cumsum_oracle(S, E, k):
+    torch.manual_seed(S + E)
+    scores = torch.softmax(torch.randn(S, E), dim=1)
+    crit, _ = routing.extract_critical(scores, top_k=k)
+    want_loc, want_cnt = _dense_locations(crit.idx_ks, E)
+    assert torch.equal(crit.loc_ks, want_loc)
+    assert torch.equal(crit[5].to(torch.int32), want_cnt)
+
+
+def test_capacity_rules_worked_example():
+    # S=10, E=4, k=2
+    torch.manual_seed(0)
+    scores = torch.softmax(torch.randn(10, 4), dim=1)
+    cap = lambda **kw: routing.extract_critical(scores, top_k=2, **kw)[0][4]
+    max_count = int(routing.extract_critical(scores, top_k=2)[0][5].max())
+    assert cap(capacity_factor=1.0) == 6
+    assert cap(capacity_factor=2.0) == 12
+    assert cap(capacity_factor=0.0) == max_count
+    assert cap(capacity_factor=-0.5) == min(max_count, 2)
+    assert cap(capacity_factor=-4.0) == min(max_count, 24)
+    assert cap(capacity_factor=1.0, alignment=4) == 8
+
+
+def test_gate_normalisation_and_l_aux():
+    torch.manual_seed(1)
+    scores = torch.softmax(torch.randn(33, 5), dim=1)
+    crit, l_aux = routing.extract_critical(scores, top_k=2)
+    g = torch.stack(crit[3])
+    assert torch.allclose(g.sum(0), torch.ones(33), atol=1e-6)
+    # gshard loss oracle
+    top1 = scores.argmax(1)
+    ce = torch.bincount(top1, minlength=5).float() * 5 / 33
+    want = (scores.sum(0) * ce).sum() / 33
+    assert torch.allclose(l_aux, want, rtol=1e-5)
+    crit2, _ = routing.extract_critical(scores, top_k=2, normalize_gate=False)
+    assert torch.allclose(torch.stack(crit2[3]), scores.gather(1, torch.topk(scores, 2, 1).indices).t())
+
+
+def test_batch_prioritized_routing_orders_by_confidence():
+    torch.manual_seed(2)
+    scores = torch.softmax(torch.randn(40, 3) * 3, dim=1)
+    crit, _ = routing.extract_critical(scores, top_k=1, batch_prioritized_routing=True, capacity_factor=0.5)
+    loc, idx, C = crit.loc_ks[0], crit.idx_ks[0], crit[4]
+    conf = scores.max(1)[0]
+    for e in range(3):
+        members = torch.nonzero(idx == e).view(-1)
+        order = members[torch.argsort(loc[members])]
+        assert torch.all(conf[order][:-1] >= conf[order][1:] - 1e-7)   # most confident tokens get the first slots
+    assert int(crit[5].sum()) == 40                                   # true counts (the reference's are wrong here)
+
+
+def _dense_moe_oracle(x, crit, is_postscore, fn):
+    """einsum-style oracle: out[s] = sum_j w * fn(buf)[slot]."""
+    E, C = crit[0], crit[4]
+    S, M = x.shape
+    buf = torch.zeros(E, C, M, dtype=x.dtype)
+    for j in range(len(crit[1])):
+        for s in range(S):
+            e, l = int(crit[1][j][s]), int(crit[2][j][s])
+            if l < C:
+                buf[e, l] = x[s] * (1.0 if is_postscore else crit[3][j][s])
+    y = fn(buf)
+    out = torch.zeros(S, y.shape[-1], dtype=x.dtype)
+    for j in range(len(crit[1])):
+        for s in range(S):
+            e, l = int(crit[1][j][s]), int(crit[2][j][s])
+            if l < C:
+                out[s] += y[e, l] * (crit[3][j][s] if is_postscore else 1.0)
+    return buf, out
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
+@pytest.mark.parametrize('is_postscore', [True, False])
+def test_encode_decode_forward_backward_vs_oracle(dtype, is_postscore):
+    torch.manual_seed(3)
+    S, E, M, k = 37, 5, 16, 2
+    logits = torch.randn(S, E, dtype=dtype, requires_grad=True)
+    x = torch.randn(S, M, dtype=dtype, requires_grad=True)
+    w = torch.randn(E, M, M, dtype=dtype)
+
+    def run(use_lib):
+        scores = torch.softmax(logits, dim=1)
+        crit, _ = routing.extract_critical(scores, top_k=k, capacity_factor=0.7)
+        fn = lambda b: torch.tanh(torch.einsum('ecm,emn->ecn', b, w))
+        if use_lib:
+            buf = moe.fast_encode(x, crit, is_postscore)
+            out = moe.fast_decode(fn(buf), crit, is_postscore)
+        else:
+            buf, out = _dense_moe_oracle(x, crit, is_postscore, fn)
+        loss = (out * torch.arange(out.numel(), dtype=dtype).view_as(out)).sum()
+        gx, gl = torch.autograd.grad(loss, [x, logits])
+        return buf.detach(), out.detach(), gx, gl
+
+    a, b = run(True), run(False)
+    tol = dict(rtol=1e-4, atol=1e-4) if dtype == torch.float32 else dict(rtol=1e-9, atol=1e-9)
+    for u, v in zip(a, b):
+        assert torch.allclose(u, v, **tol)
+
+
+def test_half_precision_cpu_fallback_path():
+    torch.manual_seed(4)
+    x = torch.randn(20, 8).to(torch.bfloat16)
+    scores = torch.softmax(torch.randn(20, 4), dim=1)
+    crit, _ = routing.extract_critical(scores, top_k=2)
+    buf = moe.fast_encode(x, crit)
+    assert buf.dtype == torch.bfloat16 and buf.shape == (4, crit[4], 8)
+    out = moe.fast_decode(buf, crit)
+    kept = torch.stack([(crit[2][j] < crit[4]).float() * crit[3][j] for j in range(2)]).sum(0)
+    assert torch.allclose(out.float(), x.float() * kept.unsqueeze(1), atol=3e-2)
+
+
+def test_plain_tuple_critical_data_is_accepted():
+    torch.manual_seed(5)
+    x = torch.randn(12, 6)
+    scores = torch.softmax(torch.randn(12, 3), dim=1)
+    crit, _ = routing.extract_critical(scores, top_k=2)
+    plain = tuple(crit)
+    assert torch.equal(moe.fast_encode(x, plain), moe.fast_encode(x, crit))
+
+
+def test_fast_cumsum_sub_one():
+    m = (torch.rand(50, 6) > 0.5).int()
+    assert torch.equal(moe.fast_cumsum_sub_one(m), torch.cumsum(m, 0) - 1)
+    with pytest.raises(Exception):
+        moe.fast_cumsum_sub_one(m, dim=1)

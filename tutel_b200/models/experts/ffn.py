@@ -131,8 +131,8 @@ class FusedExpertsNetwork(torch.nn.Module):
             y = G.grouped_linear(x, w1, b1, 'nk', row_counts)
             y = self.activation_fn(y)
             y = G.grouped_linear(y, w2, b2, 'kn', row_counts)
-        if row_counts is not None and not G.can_use_tcgen05(x, w1):
-            pass  # dense fallback computed every row; padded rows are ignored by decode anyway
+        if len(lead) > 3 and y.numel() == x.numel():
+            y = y.view(lead)    # `reserve_dims > 1`: hand the trailing dims back in the caller's shape
         return y
 
 

@@ -88,3 +88,15 @@ def use_tcgen05(t: torch.Tensor) -> bool:
     if os.environ.get('TUTEL_B200_GEMM', 'tcgen05').lower() in ('cublas', 'torch'):
         return False
     return has_cuda_ext() and is_sm100(t.device)
+
+
+# ---- native launch accounting (bench.py reports it as `gpu_launches`) ----------------------------------------------
+_LAUNCHES = [0]
+
+
+def count_launch(n: int = 1) -> None:
+    _LAUNCHES[0] += n
+
+
+def launch_count() -> int:
+    return _LAUNCHES[0]

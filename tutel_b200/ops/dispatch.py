@@ -78,6 +78,7 @@ def raw_encode(x: torch.Tensor, gates: Optional[torch.Tensor], plan: DispatchPla
     if _native_cuda(x):
         out = torch.empty([plan.E * plan.C, M], dtype=x.dtype, device=x.device)
         g = None if gates is None else gates.to(torch.float32).contiguous()
+        backend.count_launch()
         backend.require_ext().encode_rows(x, g, plan.slot_src, out, plan.k, plan.E, plan.C, 0, 0, 0, 0)
         return out
     if _cpu_native(x):
@@ -97,6 +98,7 @@ def raw_decode(buf: torch.Tensor, gates: Optional[torch.Tensor], plan: DispatchP
     buf = buf.contiguous().view(plan.E * plan.C, -1)
     if _native_cuda(buf):
         g = None if gates is None else gates.to(torch.float32).contiguous()
+        backend.count_launch()
         return backend.require_ext().decode_rows(buf, g, plan.idx_ks, plan.loc_ks, plan.E, plan.C, 0, 0)
     if _cpu_native(buf):
         g = None if gates is None else gates.to(buf.dtype).contiguous()
@@ -116,6 +118,7 @@ def raw_gate_grad(a: torch.Tensor, buf: torch.Tensor, plan: DispatchPlan) -> tor
     a = a.contiguous()
     buf = buf.contiguous().view(plan.E * plan.C, -1)
     if _native_cuda(a) and a.dtype == buf.dtype:
+        backend.count_launch()
         return backend.require_ext().gate_grad(a, buf, plan.idx_ks, plan.loc_ks, plan.E, plan.C)
     if _cpu_native(a) and a.dtype == buf.dtype:
         return backend.ext().cpu_gate_grad(a, buf, plan.idx_ks, plan.loc_ks, plan.E, plan.C)

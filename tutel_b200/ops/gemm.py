@@ -57,6 +57,7 @@ def raw_gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool
             bias = bias.to(a.dtype).contiguous()
     if aux is not None:
         aux = _prep(aux)
+    backend.count_launch()
     C.gemm(a, b, d, a_mn, b_mn, epilogue, bias, aux, row_counts, float(alpha), int(b_group_div), int(cta_group),
            int(block_n), int(d_ptr_table), int(signal_ptr_table), int(wait_flags), int(wait_rows_per_flag),
            int(wait_flags_per_group), int(wait_target), int(max_ctas))

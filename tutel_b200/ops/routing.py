@@ -44,6 +44,7 @@ def _locations(idx_ks: torch.Tensor, E: int):
     """Stable queue positions for [k, S] expert ids -> (loc [k,S] int32, counts [E] int32)."""
     k, S = idx_ks.shape
     if idx_ks.is_cuda and backend.has_cuda_ext():
+        backend.count_launch(3)
         loc, counts = backend.require_ext().route_locations(idx_ks, E, 0)[:2]
         return loc, counts
     if not idx_ks.is_cuda and backend.has_ext():
@@ -62,6 +63,7 @@ def build_slot_map(idx_ks: torch.Tensor, loc_ks: torch.Tensor, E: int, C: int) -
     """int32 [E*C]: ``token * k + choice`` occupying each slot, -1 for padding."""
     k, S = idx_ks.shape
     if idx_ks.is_cuda and backend.has_cuda_ext():
+        backend.count_launch()
         return backend.require_ext().build_slot_map(idx_ks.contiguous(), loc_ks.contiguous(), E, C)
     slot = torch.full([E * C], -1, dtype=torch.int32, device=idx_ks.device)
     valid = (loc_ks < C) & (idx_ks >= 0)
