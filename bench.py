@@ -120,16 +120,16 @@ def main():
     if args.impl == 'ours':
         from tutel_b200.ops import backend
     # ---------------- kernel-side number: inputs resident on the device ----------------
-    for _ in range(max(args.warmup, 3)):
-        step(x_dev, y_dev)
     sampler = None
     if rank == 0:
         sys.path.insert(0, ROOT)
         try:
-            from tutel_b200.utils.timers import ClockSampler
-            sampler = ClockSampler(device.index or 0).start()
+            from tutel_b200.utils.timers import ClockSampler   # plain nvidia-smi poller, no kernels involved
+            sampler = ClockSampler(device.index or 0).start()  # started early: nvidia-smi needs a moment to spin up
         except Exception:  # noqa
             sampler = None
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev, y_dev)
     sync()
     if args.impl == 'ours':
         launches0 = backend.launch_count()

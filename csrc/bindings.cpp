@@ -49,7 +49,8 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, bool a_mn, bo
           const c10::optional<at::Tensor>& bias, const c10::optional<at::Tensor>& aux,
           const c10::optional<at::Tensor>& row_counts, double alpha, int64_t b_group_div, int64_t cta_group,
           int64_t block_n, int64_t d_ptr_table, int64_t signal_ptr_table, int64_t wait_flags,
-          int64_t wait_rows_per_flag, int64_t wait_flags_per_group, int64_t wait_target, int64_t max_ctas) {
+          int64_t wait_rows_per_flag, int64_t wait_flags_per_group, int64_t wait_target, int64_t max_ctas,
+          int64_t group_rot, int64_t group_mod) {
   TORCH_CHECK(a.is_cuda() && b.is_cuda() && d.is_cuda(), "tutel_b200.gemm: CUDA tensors required");
   TORCH_CHECK(a.dim() == 3 && b.dim() == 3 && d.dim() == 3, "tutel_b200.gemm: expected 3-D operands");
   TORCH_CHECK(a.stride(2) == 1 && b.stride(2) == 1 && d.stride(2) == 1, "tutel_b200.gemm: innermost dim must be contiguous");
@@ -98,6 +99,8 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, bool a_mn, bo
   p.wait_rows_per_flag = static_cast<int>(wait_rows_per_flag);
   p.wait_flags_per_group = static_cast<int>(wait_flags_per_group);
   p.wait_target = static_cast<uint32_t>(wait_target);
+  p.group_rot = static_cast<int>(group_rot);
+  p.group_mod = static_cast<int>(group_mod != 0 ? group_mod : 1);
   const char* why = nullptr;
   cudaError_t e = tb::gemm_sm100_launch(p, cur_stream(), &why);
   TORCH_CHECK(e == cudaSuccess, "tutel_b200.gemm launch failed: ", why ? why : cudaGetErrorString(e));
@@ -137,7 +140,7 @@ at::Tensor build_slot_map(const at::Tensor& idx, const at::Tensor& loc, int64_t 
 // x [S, M]; gates float [k, S] or None; slot_src int [E*C]; out [E*C, M] (ignored rows live in dst_ptr_table).
 void encode_rows(const at::Tensor& x, const c10::optional<at::Tensor>& gates, const at::Tensor& slot_src,
                  at::Tensor& out, int64_t k, int64_t E, int64_t C, int64_t dst_ptr_table, int64_t signal_ptr_table,
-                 int64_t signal_rows, int64_t rot_chunks) {
+                 int64_t signal_rows, int64_t rot_chunks, int64_t signal_value) {
   TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous() && slot_src.is_cuda() && slot_src.is_contiguous());
   TORCH_CHECK(slot_src.scalar_type() == at::kInt && slot_src.numel() == E * C);
   const c10::cuda::CUDAGuard guard(x.device());
@@ -154,7 +157,7 @@ void encode_rows(const at::Tensor& x, const c10::optional<at::Tensor>& gates, co
                                 reinterpret_cast<const unsigned long long*>(signal_ptr_table),
                                 static_cast<int>(signal_rows), static_cast<int>(x.size(0)), static_cast<int>(E),
                                 static_cast<int>(k), static_cast<int>(C), static_cast<int>(x.size(1)), elem_type_of(x),
-                                static_cast<int>(rot_chunks), 0, cur_stream()));
+                                static_cast<int>(rot_chunks), static_cast<int>(signal_value), cur_stream()));
 }
 
 // buf [E*C, M]; gates float [k, S] or None; idx/loc int [k, S]; returns [S, M]

@@ -58,6 +58,7 @@ struct GemmArgs {
   int wait_rows_per_flag, wait_flags_per_group;
   uint32_t wait_target;
   const unsigned long long* signal_ptr_table;
+  int group_rot, group_mod;  // tile order visits group (g/mod)*mod + (g%mod + rot)%mod  (own-rank segment first)
 };
 
 namespace {
@@ -104,6 +105,20 @@ __device__ __forceinline__ TileCoord decode_tile(long long t, int tiles_m, int t
   c.m_blk = first_m + r % rows_in_band;
   c.n_blk = r / rows_in_band;
   return c;
+}
+
+// mod > 1: ascending from `rot`;  mod < -1: descending from `rot` (matches a sender that walks destinations upwards).
+__device__ __forceinline__ int rotate_group(int g, int rot, int mod) {
+  if (mod > 1) {
+    const int base = (g / mod) * mod;
+    return base + (g - base + rot) % mod;
+  }
+  if (mod < -1) {
+    const int m = -mod;
+    const int base = (g / m) * m;
+    return base + (rot + m - (g - base)) % m;
+  }
+  return g;
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -191,7 +206,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int s = 0;
     uint32_t ph = 0;
     for (long long t = tile_first; t < args.num_tiles; t += tile_step) {
-      const TileCoord tc = decode_tile<kBand>(t, args.tiles_m, args.tiles_n);
+      TileCoord tc = decode_tile<kBand>(t, args.tiles_m, args.tiles_n);
+      tc.g = rotate_group(tc.g, args.group_rot, args.group_mod);
       if (args.row_counts != nullptr && tc.m_blk * C::BM >= args.row_counts[tc.g]) continue;
       const int m0 = tc.m_blk * C::BM + static_cast<int>(cta_rank) * C::BM_CTA;
       const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * C::BN_CTA;
@@ -275,7 +291,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t b_lo0 = ((smem_b(0) >> 4) & 0x3FFFu) | ((b_lbo >> 4) << 16);
       const uint32_t idesc = args.idesc;
       for (long long t = tile_first; t < args.num_tiles; t += tile_step) {
-        const TileCoord tc = decode_tile<kBand>(t, args.tiles_m, args.tiles_n);
+        TileCoord tc = decode_tile<kBand>(t, args.tiles_m, args.tiles_n);
+      tc.g = rotate_group(tc.g, args.group_rot, args.group_mod);
         if (args.row_counts != nullptr && tc.m_blk * C::BM >= args.row_counts[tc.g]) continue;
         ptx::mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
         ptx::tc_fence_after();
@@ -309,7 +326,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool out16 = (args.out_dtype != DT_FP32);
     const bool out_bf16 = (args.out_dtype == DT_BF16);
     for (long long t = tile_first; t < args.num_tiles; t += tile_step) {
-      const TileCoord tc = decode_tile<kBand>(t, args.tiles_m, args.tiles_n);
+      TileCoord tc = decode_tile<kBand>(t, args.tiles_m, args.tiles_n);
+      tc.g = rotate_group(tc.g, args.group_rot, args.group_mod);
       int m_valid = args.M;
       if (args.row_counts != nullptr) {
         m_valid = min(args.M, args.row_counts[tc.g]);
@@ -590,6 +608,7 @@ cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const c
   a.wait_flags = p.wait_flags; a.wait_rows_per_flag = p.wait_rows_per_flag > 0 ? p.wait_rows_per_flag : bm;
   a.wait_flags_per_group = p.wait_flags_per_group; a.wait_target = p.wait_target;
   a.signal_ptr_table = p.signal_ptr_table;
+  a.group_rot = p.group_rot; a.group_mod = p.group_mod;
 
   CUtensorMap ta, tb_;
   const int gB = (p.G + a.b_group_div - 1) / a.b_group_div;

@@ -60,6 +60,9 @@ struct GemmProblem {
   // Optional combine fusion: after an output tile of group g is stored, signal_ptr_table[g] (a uint32 counter,
   // usually in a peer's memory) is incremented with release.sys semantics.
   const unsigned long long* signal_ptr_table = nullptr;
+  // Tile order: group g is visited as (g/mod)*mod + (g%mod + rot)%mod, so a rank can start with the segment whose
+  // rows it produced itself while the peers' rows are still in flight.
+  int group_rot = 0, group_mod = 1;
 
   // Tuning: cta_group (1 or 2, 0 = auto), BN (128 or 256, 0 = auto)
   int cta_group = 0;

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kEncThreads)
 encode_rows_kernel(const T* __restrict__ x, const float* __restrict__ gates, const int* __restrict__ slot_src,
                    T* __restrict__ out, const unsigned long long* __restrict__ dst_ptr_table,
                    const unsigned long long* __restrict__ signal_ptr_table, int chunk_rows, int S, int E, int k, int C,
-                   int M, int rot_chunks) {
+                   int M, int rot_chunks, uint32_t signal_value) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int chunks_per_expert = (C + chunk_rows - 1) / chunk_rows;
@@ -269,7 +269,9 @@ encode_rows_kernel(const T* __restrict__ x, const float* __restrict__ gates, con
       __syncthreads();  // every warp's stores of this chunk are issued and ordered before the release below
       if (threadIdx.x == 0) {
         ptx::fence_acq_rel_sys();
-        ptx::red_add_release_sys(reinterpret_cast<uint32_t*>(signal_ptr_table[e]) + r0 / chunk_rows, 1u);
+        uint32_t* flag = reinterpret_cast<uint32_t*>(signal_ptr_table[e]) + r0 / chunk_rows;
+        if (signal_value != 0u) ptx::st_release_sys(flag, signal_value);
+        else ptx::red_add_release_sys(flag, 1u);
       }
     }
   }
@@ -502,33 +504,36 @@ cudaError_t build_slot_map(const int* idx, const int* loc, int* slot_src, int S,
 template <typename T>
 static cudaError_t encode_rows_t(const void* x, const void* gates, const int* slot_src, void* out,
                                  const unsigned long long* dst_ptr_table, const unsigned long long* signal_ptr_table,
-                                 int signal_rows, int S, int E, int k, int C, int M, int rot, cudaStream_t stream) {
+                                 int signal_rows, int S, int E, int k, int C, int M, int rot, int signal_value, int max_blocks,
+                                 cudaStream_t stream) {
   if (E <= 0 || C <= 0 || M <= 0) return cudaSuccess;
   const int chunk_rows = signal_rows > 0 ? signal_rows : 16;
   const long long chunks = static_cast<long long>(E) * ((C + chunk_rows - 1) / chunk_rows);
-  const int grid = static_cast<int>(chunks < 4LL * num_sms() ? chunks : 4LL * num_sms());
+  int grid = static_cast<int>(chunks < 4LL * num_sms() ? chunks : 4LL * num_sms());
+  if (max_blocks > 0 && grid > max_blocks) grid = max_blocks;
   const bool vec = (M % Vec<T>::N == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                    (dst_ptr_table != nullptr || (reinterpret_cast<uintptr_t>(out) & 15) == 0);
   if (vec)
     encode_rows_kernel<T, true><<<grid, kEncThreads, 0, stream>>>(
         static_cast<const T*>(x), static_cast<const float*>(gates), slot_src, static_cast<T*>(out), dst_ptr_table,
-        signal_ptr_table, chunk_rows, S, E, k, C, M, rot);
+        signal_ptr_table, chunk_rows, S, E, k, C, M, rot, static_cast<uint32_t>(signal_value));
   else
     encode_rows_kernel<T, false><<<grid, kEncThreads, 0, stream>>>(
         static_cast<const T*>(x), static_cast<const float*>(gates), slot_src, static_cast<T*>(out), dst_ptr_table,
-        signal_ptr_table, chunk_rows, S, E, k, C, M, rot);
+        signal_ptr_table, chunk_rows, S, E, k, C, M, rot, static_cast<uint32_t>(signal_value));
   return cudaGetLastError();
 }
 
 cudaError_t encode_rows(const void* x, const void* gates, const int* slot_src, void* out,
                         const unsigned long long* dst_ptr_table, const unsigned long long* signal_ptr_table,
-                        int signal_rows, int S, int E, int k, int C, int M, int elem_type, int row_begin, int row_end,
-                        cudaStream_t stream) {
-  (void)row_end;
+                        int signal_rows, int S, int E, int k, int C, int M, int elem_type, int rot_chunks,
+                        int signal_value, cudaStream_t stream) {
+  // remote pushes leave most SMs to the concurrently running expert GEMM
+  const int max_blocks = dst_ptr_table != nullptr ? 96 : 0;
   switch (elem_type) {
-    case ET_F32: return encode_rows_t<float>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, signal_rows, S, E, k, C, M, row_begin, stream);
-    case ET_F16: return encode_rows_t<__half>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, signal_rows, S, E, k, C, M, row_begin, stream);
-    case ET_BF16: return encode_rows_t<__nv_bfloat16>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, signal_rows, S, E, k, C, M, row_begin, stream);
+    case ET_F32: return encode_rows_t<float>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, signal_rows, S, E, k, C, M, rot_chunks, signal_value, max_blocks, stream);
+    case ET_F16: return encode_rows_t<__half>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, signal_rows, S, E, k, C, M, rot_chunks, signal_value, max_blocks, stream);
+    case ET_BF16: return encode_rows_t<__nv_bfloat16>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, signal_rows, S, E, k, C, M, rot_chunks, signal_value, max_blocks, stream);
   }
   return cudaErrorInvalidValue;
 }

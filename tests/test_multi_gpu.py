@@ -1,0 +1,32 @@
+"""Multi-GPU tests (NVLink P2P collectives, fused dispatch/combine engine) - need >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from helpers import ROOT, next_port
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _run(which, nproc):
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=%d' % nproc, '--master-addr',
+           '127.0.0.1', '--master-port', str(next_port()), os.path.join(ROOT, 'tests', 'workers', 'p2p_worker.py'), which]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert p.returncode == 0 and 'WORKER_OK' in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason='needs 2 GPUs')
+def test_p2p_collectives_match_nccl():
+    _run('coll', 2)
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason='needs 2 GPUs')
+def test_fused_engine_matches_nccl_path():
+    _run('fused', 2)

@@ -1,0 +1,120 @@
+"""Worker for multi-GPU tests: P2P collectives vs torch.distributed (NCCL), fused MoE path vs NCCL path."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from tutel_b200 import moe, net, system  # noqa: E402
+from tutel_b200.parallel import p2p  # noqa: E402
+
+
+def check(name, ok):
+    r = dist.get_rank()
+    print('[rank %d] %s: %s' % (r, name, 'OK' if ok else 'FAIL'), flush=True)
+    if not ok:
+        raise SystemExit(3)
+
+
+def test_collectives(env):
+    W, r, dev = env.global_size, env.global_rank, env.local_device
+    t = p2p.transport_for(None)
+    check('transport', t is not None)
+    torch.manual_seed(100 + r)
+    for n in (W * 4, W * 1000, W * 65536 + W * 3):
+        x = torch.randn(n, device=dev)
+        ref = torch.empty_like(x)
+        dist.all_to_all_single(ref, x)
+        check('all_to_all n=%d' % n, torch.equal(net.simple_all_to_all(x), ref))
+    x = torch.randn(W, 3, 5, device=dev).bfloat16()
+    ref = torch.empty_like(x)
+    dist.all_to_all_single(ref, x)
+    check('all_to_all bf16', torch.equal(net.simple_all_to_all(x), ref))
+    y = torch.randn(7, 3, device=dev)
+    ref = torch.empty(W * 7, 3, device=dev)
+    dist.all_gather_into_tensor(ref, y)
+    check('all_gather', torch.equal(net.simple_all_gather(y), ref))
+    z = torch.randn(W * 6, 4, device=dev)
+    ref = z.clone()
+    dist.all_reduce(ref)
+    check('all_reduce', torch.allclose(net.simple_all_reduce(z), ref, atol=1e-5))
+    ref_rs = ref.view(W, -1)[r].view(6, 4)
+    check('reduce_scatter', torch.allclose(net.simple_reduce_scatter(z), ref_rs, atol=1e-5))
+    zm = torch.randn(33, device=dev)
+    refm = zm.clone()
+    dist.all_reduce(refm, op=dist.ReduceOp.MAX)
+    check('all_reduce max', torch.equal(net.simple_all_reduce(zm, op=dist.ReduceOp.MAX), refm))
+    # ragged
+    counts = [(r + p) % 3 + 1 for p in range(W)]
+    data = torch.arange(sum(counts), device=dev, dtype=torch.float32) + 100 * r
+    (out,), sizes = net.batch_all_to_all_v([data], counts)
+    want = []
+    for s in range(W):
+        c = [(s + p) % 3 + 1 for p in range(W)]
+        full = torch.arange(sum(c), dtype=torch.float32) + 100 * s
+        off = sum(c[:r])
+        want.append(full[off:off + c[r]])
+    check('all_to_all_v', torch.equal(out.cpu(), torch.cat(want)) and sizes.tolist() == [len(w) for w in want])
+    mine = torch.full([r + 2], float(r), device=dev)
+    (g,), gs = net.batch_all_gather_v([mine])
+    check('all_gather_v', torch.equal(g.cpu(), torch.cat([torch.full([s + 2], float(s)) for s in range(W)])))
+    # autograd all_to_all round trip
+    a = torch.randn(W * 2, 3, 4, device=dev, requires_grad=True)
+    b = net.all_to_all(net.all_to_all(a, 1, 0), 0, 1)
+    b.sum().backward()
+    check('all_to_all autograd', torch.equal(b, a) and torch.equal(a.grad, torch.ones_like(a)))
+
+
+def run_layer(env, fused, dtype, nle, steps=3, overlap=1, model_dim=256, hidden=512, tokens=512):
+    os.environ['TUTEL_B200_FUSED'] = '1' if fused else '0'
+    r, dev = env.global_rank, env.local_device
+    torch.manual_seed(7)
+    layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2, 'capacity_factor': 1.5}, model_dim=model_dim,
+                          experts={'type': 'ffn', 'num_experts_per_device': nle, 'hidden_size_per_expert': hidden,
+                                   'activation_fn': lambda t: F.relu(t)},
+                          seeds=(1, r + 1, 1), a2a_ffn_overlap_degree=overlap).to(dev).to(dtype)
+    opt = torch.optim.SGD(layer.parameters(), lr=1e-2)
+    torch.manual_seed(50 + r)
+    x = torch.randn(tokens, model_dim, device=dev).to(dtype)
+    losses, grads = [], None
+    for _ in range(steps):
+        opt.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        y = layer(xi)
+        loss = y.float().pow(2).mean() + 0.01 * y.l_aux.float()
+        loss.backward()
+        losses.append(float(loss))
+        grads = xi.grad.float().clone()
+        opt.step()
+    return losses, grads, y.float().detach()
+
+
+def test_fused_vs_nccl(env):
+    for dtype in (torch.bfloat16,):
+        for nle in (1, 2):
+            for overlap in (1, 2):
+                a = run_layer(env, True, dtype, nle, overlap=overlap)
+                b = run_layer(env, False, dtype, nle, overlap=1)
+                ok = all(abs(u - v) <= 2e-2 * max(1.0, abs(v)) for u, v in zip(a[0], b[0]))
+                ok = ok and torch.allclose(a[2], b[2], atol=3e-2, rtol=3e-2) and torch.allclose(a[1], b[1], atol=3e-2, rtol=5e-2)
+                if not ok:
+                    print('losses', a[0], b[0], (a[2] - b[2]).abs().max().item(), (a[1] - b[1]).abs().max().item(), flush=True)
+                check('fused==nccl nle=%d d=%d' % (nle, overlap), ok)
+
+
+def main():
+    env = system.init_data_model_parallel(backend='nccl')
+    which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+    if which in ('all', 'coll'):
+        test_collectives(env)
+    if which in ('all', 'fused'):
+        test_fused_vs_nccl(env)
+    dist.barrier()
+    if env.global_rank == 0:
+        print('WORKER_OK', flush=True)
+
+
+if __name__ == '__main__':
+    main()

@@ -38,7 +38,7 @@ def raw_gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool
              out_dtype: Optional[torch.dtype] = None, alpha: float = 1.0, b_group_div: int = 1, cta_group: int = 0,
              block_n: int = 0, d_ptr_table: int = 0, signal_ptr_table: int = 0, wait_flags: int = 0,
              wait_rows_per_flag: int = 0, wait_flags_per_group: int = 0, wait_target: int = 0,
-             max_ctas: int = 0) -> torch.Tensor:
+             max_ctas: int = 0, group_rot: int = 0, group_mod: int = 1) -> torch.Tensor:
     """D[g] = epilogue(A[g] @ B[g // b_group_div]).
 
     ``a``: ``[G, M, K]`` (or ``[G, K, M]`` when ``a_mn``);  ``b``: ``[Gb, N, K]`` (or ``[Gb, K, N]`` when ``b_mn``).
@@ -60,7 +60,7 @@ def raw_gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool
     backend.count_launch()
     C.gemm(a, b, d, a_mn, b_mn, epilogue, bias, aux, row_counts, float(alpha), int(b_group_div), int(cta_group),
            int(block_n), int(d_ptr_table), int(signal_ptr_table), int(wait_flags), int(wait_rows_per_flag),
-           int(wait_flags_per_group), int(wait_target), int(max_ctas))
+           int(wait_flags_per_group), int(wait_target), int(max_ctas), int(group_rot), int(group_mod))
     return out
 
 

@@ -1,5 +1,308 @@
-"""Placeholder (replaced below in this commit series)."""
+"""NVLink-fused expert-parallel engine: dispatch+GEMM1 and GEMM2+combine with no separate all-to-all.
+
+This is the B200-native replacement of the reference's ``all_to_all -> experts -> all_to_all`` sequence
+(tutel/impls/moe_layer.py:349-351) and of its chunked NCCL overlap scheduler (tutel/impls/overlap.py,
+tutel/custom/custom_kernel.cpp:520-654).  Per forward pass and rank (W ranks, El local experts, capacity C):
+
+  comm stream   encode kernel: gathers this rank's tokens slot by slot and *stores them straight into the
+                destination expert GPU's receive buffer* ``X_recv[El, W(src), C, M]`` over NVLink, publishing an
+                epoch flag per row chunk with ``st.release.sys``                       (csrc/moe_kernels.cu)
+  main stream   GEMM1 (tcgen05): its TMA producer ``ld.acquire.sys``-polls the flags of exactly the rows of the
+                tile it is about to load, so tiles are multiplied as they arrive - own-rank rows first.
+                GEMM2 (tcgen05): the epilogue stores every output tile *directly into the source GPU's* combine
+                buffer ``Y_comb[E, C, Mout]`` and bumps a ``red.release.sys`` counter per expert.
+                decode kernel: acquires the counters of the experts a token used and sums its k rows.
+
+Backward mirrors this (output gradients are dispatched, dgrad/wgrad GEMMs run as rows arrive, input gradients are
+combined), so one training step issues 4 fused transfers and never calls NCCL for tokens.
+``a2a_ffn_overlap_degree`` selects the flag granularity (rows per arrival flag = C / d, at least one MMA tile).
+
+Buffers live in the symmetric heap (parallel/p2p.py).  Each layer owns a small ring of buffer sets; a set stays
+reserved from forward until its backward finished and sets are re-used least-recently-used first, which - together
+with the data dependencies between ranks - guarantees that no peer can overwrite rows that are still being read.
+"""
+from __future__ import annotations
+
+import os
+from typing import Any, Dict, List, Optional
+
+import torch
+
+from ..ops import backend
+from ..ops import gemm as G
+from ..ops.dispatch import DispatchPlan
+from . import p2p
+
+_FLAGS_PER_SEG = 64          # arrival flags per (expert, source) segment
+_MIN_RING = 2
+_MAX_RING = 6
 
 
-def engine_for(layer, x, crit, d):
-    return None
+def _enabled() -> bool:
+    return os.environ.get('TUTEL_B200_FUSED', '1') not in ('0', 'off', 'false')
+
+
+class _BufferSet:
+    """One set of symmetric buffers + flag areas (identical offsets on every rank)."""
+
+    def __init__(self, eng: 'FusedEngine', index: int, C: int):
+        t, es = eng.t, eng.es
+        W, El, E, M, Mo = eng.W, eng.El, eng.E, eng.M, eng.Mo
+        tag = '%s/set%d/C%d' % (eng.tag, index, C)
+        self.C = C
+        self.x_recv = t.alloc(tag + '/x_recv', El * W * C * M * es)
+        self.y_comb = t.alloc(tag + '/y_comb', E * C * Mo * es)
+        self.dy_recv = t.alloc(tag + '/dy_recv', El * W * C * Mo * es)
+        self.dx_comb = t.alloc(tag + '/dx_comb', E * C * M * es)
+        self.f_disp = t.ctrl_alloc(tag + '/f_disp', El * W * _FLAGS_PER_SEG * 4)
+        self.f_comb = t.ctrl_alloc(tag + '/f_comb', E * 4)
+        self.b_disp = t.ctrl_alloc(tag + '/b_disp', El * W * _FLAGS_PER_SEG * 4)
+        self.b_comb = t.ctrl_alloc(tag + '/b_comb', E * 4)
+        self.epoch = 0                # published by the encode kernels (one writer per flag)
+        self.comb_total = [0, 0]      # cumulative tile counts expected on f_comb / b_comb
+        self.busy = False
+        self.last_used = -1
+        self.tables: Dict[Any, torch.Tensor] = {}
+
+    @staticmethod
+    def bytes_needed(eng: 'FusedEngine', C: int) -> int:
+        return 2 * (eng.El * eng.W * C * (eng.M + eng.Mo)) * eng.es + 4096
+
+
+class FusedEngine:
+    def __init__(self, layer, transport: 'p2p.P2PTransport', dtype: torch.dtype):
+        ex = layer.experts
+        self.t = transport
+        self.W, self.rank = transport.world, transport.rank
+        self.El, self.E = layer.num_local_experts, layer.num_global_experts
+        self.M, self.H, self.Mo = layer.model_dim, ex.hidden_size, ex.output_dim
+        self.dtype, self.es = dtype, torch.empty((), dtype=dtype).element_size()
+        self.tag = 'moe%x' % id(layer)
+        self.sets: Dict[int, List[_BufferSet]] = {}
+        self.clock = 0
+        self.side = torch.cuda.Stream()
+        self.disabled_for: set = set()
+
+    # ---- buffer ring ------------------------------------------------------------------------------------------
+    def acquire(self, C: int, hold: bool) -> Optional[_BufferSet]:
+        ring = self.sets.setdefault(C, [])
+        free = [s for s in ring if not s.busy]
+        if len(ring) < _MIN_RING or not free:
+            if len(ring) >= _MAX_RING and not free:
+                # forwards whose backward never ran keep their set reserved; recycle the oldest one
+                return self._take(min(ring, key=lambda s: s.last_used), hold)
+            if not self.t.can_alloc(_BufferSet.bytes_needed(self, C)):
+                return None if not free else self._take(min(free, key=lambda s: s.last_used), hold)
+            ring.append(_BufferSet(self, len(ring), C))
+            return self._take(ring[-1], hold)
+        return self._take(min(free, key=lambda s: s.last_used), hold)
+
+    def _take(self, s: _BufferSet, hold: bool) -> _BufferSet:
+        self.clock += 1
+        s.last_used, s.busy = self.clock, hold
+        return s
+
+    # ---- pointer tables (device int64 arrays, cached per buffer set) ------------------------------------------------
+    def _table(self, s: _BufferSet, key, values: List[int]) -> int:
+        tab = s.tables.get(key)
+        if tab is None:
+            tab = torch.tensor(values, dtype=torch.int64, device='cuda')
+            s.tables[key] = tab
+        return tab.data_ptr()
+
+    def push_tables(self, s: _BufferSet, data_off: int, flag_off: int, width: int):
+        """Encode side: expert e's rows go to rank e//El, segment (e%El, my rank)."""
+        C, W, El, rank, es = s.C, self.W, self.El, self.rank, self.es
+        dst = [self.t.base_ptr(e // El) + data_off + ((e % El) * W + rank) * C * width * es for e in range(self.E)]
+        sig = [self.t.base_ptr(e // El) + flag_off + ((e % El) * W + rank) * _FLAGS_PER_SEG * 4 for e in range(self.E)]
+        return self._table(s, ('pd', data_off, width), dst), self._table(s, ('ps', flag_off), sig)
+
+    def combine_tables(self, s: _BufferSet, data_off: int, flag_off: int, width: int):
+        """GEMM epilogue side: group g = (local expert, source rank) is written into the source rank's buffer."""
+        C, W, El, rank, es = s.C, self.W, self.El, self.rank, self.es
+        dst, sig = [], []
+        for g in range(El * W):
+            el, src = divmod(g, W)
+            e = rank * El + el
+            dst.append(self.t.base_ptr(src) + data_off + e * C * width * es)
+            sig.append(self.t.base_ptr(src) + flag_off + e * 4)
+        return self._table(s, ('cd', data_off, width), dst), self._table(s, ('cs', flag_off), sig)
+
+    def chunk_rows(self, C: int, d: int) -> int:
+        rows = max(256, -(-C // max(d, 1)))
+        rows = max(rows, -(-C // _FLAGS_PER_SEG))
+        return (rows + 255) // 256 * 256
+
+    @staticmethod
+    def tile_counts(C: int, N: int):
+        cg = 2 if C > 128 else 1
+        bn = 256 if N > 128 else 128
+        return cg, bn, (-(-C // (128 * cg))) * (-(-N // bn))
+
+
+_ENGINES: Dict[int, Optional[FusedEngine]] = {}
+
+
+def engine_for(layer, x: torch.Tensor, crit, d: int):
+    """Return a runnable fused engine for this call, or None when the generic path must be used."""
+    if not _enabled() or not backend.use_tcgen05(x):
+        return None
+    ex = layer.experts
+    from ..models.experts.ffn import FusedExpertsNetwork
+    if not isinstance(ex, FusedExpertsNetwork) or ex._act_kind != 'relu' or ex.skip_expert:
+        return None
+    if layer.sharded_count != 1 or layer.adaptive_degree != 1 or layer.megablocks_size > 0:
+        return None
+    if ex.batched_fc1_w.dtype != x.dtype or (layer.model_dim % 8) or (ex.hidden_size % 8) or (ex.output_dim % 8):
+        return None
+    key = id(layer)
+    if key not in _ENGINES:
+        t = p2p.transport_for(layer.group)
+        _ENGINES[key] = FusedEngine(layer, t, x.dtype) if t is not None else None
+    eng = _ENGINES[key]
+    if eng is None or eng.dtype != x.dtype:
+        return None
+    return _Runner(eng, d)
+
+
+class _Runner:
+    def __init__(self, eng: FusedEngine, d: int):
+        self.eng, self.d = eng, d
+
+    def run(self, layer, x: torch.Tensor, crit) -> torch.Tensor:
+        eng = self.eng
+        plan = DispatchPlan.from_critical(crit)
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in layer.parameters()))
+        bufs = eng.acquire(plan.C, hold=need_grad)
+        if bufs is None:
+            raise RuntimeError('tutel_b200: symmetric heap too small for the fused MoE buffers; raise TUTEL_B200_HEAP_MB '
+                               'or set TUTEL_B200_FUSED=0')
+        ex = layer.experts
+        gates = crit.gates_ks if hasattr(crit, 'gates_ks') else torch.stack([g.view(-1) for g in crit[3]])
+        return _FusedMoE.apply(eng, bufs, plan, self.d, layer.is_postscore, x, gates, ex.batched_fc1_w,
+                               ex.batched_fc1_bias, ex.batched_fc2_w, ex.batched_fc2_bias)
+
+
+def _push(eng: FusedEngine, bufs: _BufferSet, plan: DispatchPlan, src: torch.Tensor, gates_f32, data_off: int,
+          flag_off: int, width: int, chunk: int) -> torch.cuda.Event:
+    """Launch the scatter-and-send kernel on the side stream; returns an event recorded after it."""
+    C_ext = backend.require_ext()
+    dst_tab, sig_tab = eng.push_tables(bufs, data_off, flag_off, width)
+    cur = torch.cuda.current_stream()
+    eng.side.wait_stream(cur)
+    chunks_per_expert = -(-plan.C // chunk)
+    with torch.cuda.stream(eng.side):
+        backend.count_launch()
+        C_ext.encode_rows(src, gates_f32, plan.slot_src, src, plan.k, plan.E, plan.C, dst_tab, sig_tab, chunk,
+                          eng.rank * eng.El * chunks_per_expert, bufs.epoch)
+        ev = torch.cuda.Event()
+        ev.record(eng.side)
+    src.record_stream(eng.side)
+    plan.slot_src.record_stream(eng.side)
+    if gates_f32 is not None:
+        gates_f32.record_stream(eng.side)
+    return ev
+
+
+class _FusedMoE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx: Any, eng: FusedEngine, bufs: _BufferSet, plan: DispatchPlan, d: int, is_postscore: bool,
+                x, gates, w1, b1, w2, b2):
+        t, W, El, E, rank = eng.t, eng.W, eng.El, eng.E, eng.rank
+        C, M, H, Mo = plan.C, eng.M, eng.H, eng.Mo
+        chunk = eng.chunk_rows(C, d)
+        bufs.epoch += 1
+        gates_f32 = gates.detach().to(torch.float32).contiguous()
+        base = t.base_ptr(rank)
+
+        # (1) dispatch: tokens -> expert GPUs' X_recv (side stream, overlaps GEMM1)
+        ev = _push(eng, bufs, plan, x, None if is_postscore else gates_f32, bufs.x_recv, bufs.f_disp, M, chunk)
+
+        # (2) GEMM1 + bias + ReLU on rows as they arrive
+        x_recv = t.view(bufs.x_recv, [El * W, C, M], eng.dtype)
+        cg, bn1, _ = eng.tile_counts(C, H)
+        act = G.raw_gemm(x_recv, w1, epilogue=G.EPI_BIAS_RELU, bias=b1, b_group_div=W, cta_group=cg, block_n=bn1,
+                         wait_flags=base + bufs.f_disp, wait_rows_per_flag=chunk, wait_flags_per_group=_FLAGS_PER_SEG,
+                         wait_target=bufs.epoch, group_rot=rank, group_mod=-W)
+
+        # (3) GEMM2 + bias, epilogue writes into the source GPUs' Y_comb and signals per expert
+        cg2, bn2, tiles2 = eng.tile_counts(C, Mo)
+        d_tab, s_tab = eng.combine_tables(bufs, bufs.y_comb, bufs.f_comb, Mo)
+        y_comb = t.view(bufs.y_comb, [E, C, Mo], eng.dtype)
+        G.raw_gemm(act, w2, b_mn=True, epilogue=G.EPI_BIAS if b2 is not None else G.EPI_NONE, bias=b2, b_group_div=W,
+                   out=y_comb, cta_group=cg2, block_n=bn2, d_ptr_table=d_tab, signal_ptr_table=s_tab, group_rot=rank,
+                   group_mod=-W)
+        bufs.comb_total[0] += tiles2
+
+        # (4) combine: weighted sum of each token's k rows once their experts have delivered
+        backend.count_launch()
+        out = backend.require_ext().decode_rows(y_comb.view(E * C, Mo), gates_f32 if is_postscore else None, plan.idx_ks,
+                                                plan.loc_ks, E, C, base + bufs.f_comb, bufs.comb_total[0])
+        torch.cuda.current_stream().wait_event(ev)
+
+        ctx.eng, ctx.bufs, ctx.plan, ctx.d, ctx.is_postscore = eng, bufs, plan, d, is_postscore
+        ctx.has_b1, ctx.has_b2 = b1 is not None, b2 is not None
+        ctx.save_for_backward(x, gates, w1, w2, act)
+        if not bufs.busy:
+            pass  # inference: the set was never reserved
+        return out
+
+    @staticmethod
+    def backward(ctx: Any, dout: torch.Tensor):
+        eng, bufs, plan, d, is_postscore = ctx.eng, ctx.bufs, ctx.plan, ctx.d, ctx.is_postscore
+        x, gates, w1, w2, act = ctx.saved_tensors
+        t, W, El, E, rank = eng.t, eng.W, eng.El, eng.E, eng.rank
+        C, M, H, Mo = plan.C, eng.M, eng.H, eng.Mo
+        C_ext = backend.require_ext()
+        chunk = eng.chunk_rows(C, d)
+        base = t.base_ptr(rank)
+        dout = dout.contiguous()
+        gates_f32 = gates.detach().to(torch.float32).contiguous()
+        x_recv = t.view(bufs.x_recv, [El * W, C, M], eng.dtype)
+        y_comb = t.view(bufs.y_comb, [E * C, Mo], eng.dtype)
+
+        # (a) gate gradients of the combine:  <dout[s], y[slot_j(s)]>
+        dgates = None
+        if is_postscore and ctx.needs_input_grad[6]:
+            backend.count_launch()
+            dgates = C_ext.gate_grad(dout, y_comb, plan.idx_ks, plan.loc_ks, E, C).to(gates.dtype)
+
+        # (b) dispatch the output gradients to the expert GPUs (decode.bwd == encode of dout)
+        bufs.epoch += 1
+        ev = _push(eng, bufs, plan, dout, gates_f32 if is_postscore else None, bufs.dy_recv, bufs.b_disp, Mo, chunk)
+        dy_recv = t.view(bufs.dy_recv, [El * W, C, Mo], eng.dtype)
+
+        # (c) dh = (dy @ W2^T) * relu'(act)   as rows arrive
+        cg, bnh, _ = eng.tile_counts(C, H)
+        dh = G.raw_gemm(dy_recv, w2, epilogue=G.EPI_RELU_BWD, aux=act, b_group_div=W, cta_group=cg, block_n=bnh,
+                        wait_flags=base + bufs.b_disp, wait_rows_per_flag=chunk, wait_flags_per_group=_FLAGS_PER_SEG,
+                        wait_target=bufs.epoch, group_rot=rank, group_mod=-W)
+
+        # (e) dX_e = dh @ W1, epilogue pushes into the source GPUs' dX_comb
+        cgx, bnx, tilesx = eng.tile_counts(C, M)
+        d_tab, s_tab = eng.combine_tables(bufs, bufs.dx_comb, bufs.b_comb, M)
+        dx_comb = t.view(bufs.dx_comb, [E, C, M], eng.dtype)
+        G.raw_gemm(dh, w1, b_mn=True, b_group_div=W, out=dx_comb, cta_group=cgx, block_n=bnx, d_ptr_table=d_tab,
+                   signal_ptr_table=s_tab, group_rot=rank, group_mod=-W)
+        bufs.comb_total[1] += tilesx
+
+        # (d, f) weight gradients over all W*C received rows of each local expert
+        act_e, dh_e = act.view(El, W * C, H), dh.view(El, W * C, H)
+        dw2 = G.raw_gemm(act_e, dy_recv.view(El, W * C, Mo), a_mn=True, b_mn=True) if ctx.needs_input_grad[9] else None
+        dw1 = G.raw_gemm(dh_e, x_recv.view(El, W * C, M), a_mn=True, b_mn=True) if ctx.needs_input_grad[7] else None
+        db1 = dh_e.sum(dim=1, dtype=torch.float32).to(dh.dtype) if ctx.has_b1 and ctx.needs_input_grad[8] else None
+        db2 = (dy_recv.view(El, W * C, Mo).sum(dim=1, dtype=torch.float32).to(dh.dtype)
+               if ctx.has_b2 and ctx.needs_input_grad[10] else None)
+
+        # (g) combine the input gradients (encode.bwd == decode of the gradient buffer)
+        dx = None
+        if ctx.needs_input_grad[5] or not is_postscore:
+            backend.count_launch()
+            dx = C_ext.decode_rows(dx_comb.view(E * C, M), None if is_postscore else gates_f32, plan.idx_ks, plan.loc_ks,
+                                   E, C, base + bufs.b_comb, bufs.comb_total[1])
+        if not is_postscore and ctx.needs_input_grad[6]:
+            backend.count_launch()
+            dgates = C_ext.gate_grad(x, dx_comb.view(E * C, M), plan.idx_ks, plan.loc_ks, E, C).to(gates.dtype)
+        torch.cuda.current_stream().wait_event(ev)
+        bufs.busy = False
+        return None, None, None, None, None, dx, dgates, dw1, db1, dw2, db2

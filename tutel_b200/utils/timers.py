@@ -33,7 +33,7 @@ class ClockSampler:
               'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
               'clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, gpu_index: int = 0, period_ms: int = 100):
+    def __init__(self, gpu_index: int = 0, period_ms: int = 20):
         self.gpu_index, self.period_ms = gpu_index, period_ms
         self.samples = []
         self._proc = None
