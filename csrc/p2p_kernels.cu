@@ -22,8 +22,8 @@ constexpr int kPushThreads = 512;
 
 __global__ void __launch_bounds__(kPushThreads)
 p2p_push_kernel(const uint8_t* __restrict__ src, const PushPlan plan, const unsigned long long* __restrict__ peer_table,
-                long long dst_heap_off, long long ready_off, long long done_off, int rank, int world, uint32_t epoch,
-                int blocks_per_peer) {
+                long long dst_heap_off, long long ready_off, long long done_off, long long scratch_off, int rank,
+                int world, uint32_t epoch, int blocks_per_peer) {
   const int pi = blockIdx.x / blocks_per_peer;           // which peer (rotated so that traffic is spread)
   const int sub = blockIdx.x - pi * blocks_per_peer;     // which slice of that peer's payload
   const int peer = (rank + pi) % world;
@@ -66,16 +66,22 @@ p2p_push_kernel(const uint8_t* __restrict__ src, const PushPlan plan, const unsi
     const long long b0 = per * sub, b1 = min(total, b0 + per);
     for (long long b = b0 + threadIdx.x; b < b1; b += kPushThreads) d[b] = s[b];
   }
-  // (3) completion
+  // (3) completion: the LAST block working for this peer publishes one release.sys increment, so the receiver's
+  //     target is simply the call number (it does not need to know how many blocks the sender used)
   __syncthreads();
   if (threadIdx.x == 0) {
-    ptx::fence_acq_rel_sys();
-    ptx::red_add_release_sys(reinterpret_cast<uint32_t*>(peer_base + done_off) + rank, 1u);
+    uint32_t* local_cnt = reinterpret_cast<uint32_t*>(my_base + scratch_off) + peer;
+    uint32_t prev;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(local_cnt) : "memory");
+    if (prev == static_cast<uint32_t>(blocks_per_peer) - 1u) {
+      *local_cnt = 0u;  // every block of this call has arrived; re-arm for the next call (stream-ordered)
+      ptx::fence_acq_rel_sys();
+      ptx::red_add_release_sys(reinterpret_cast<uint32_t*>(peer_base + done_off) + rank, 1u);
+    }
   }
   // (4) inbound completion: block i (< world) watches source i
   if (blockIdx.x < world && threadIdx.x == 0)
-    ptx::wait_flag_ge_sys(reinterpret_cast<const uint32_t*>(my_base + done_off) + blockIdx.x,
-                          epoch * static_cast<uint32_t>(blocks_per_peer));
+    ptx::wait_flag_ge_sys(reinterpret_cast<const uint32_t*>(my_base + done_off) + blockIdx.x, epoch);
 }
 
 template <typename T>
@@ -121,13 +127,13 @@ __global__ void p2p_barrier_kernel(const unsigned long long* __restrict__ peer_t
 }  // namespace
 
 cudaError_t p2p_push(const void* src, const PushPlan& plan, const unsigned long long* peer_table,
-                     long long dst_heap_off, long long ready_off, long long done_off, int rank, int world,
-                     uint32_t epoch, int blocks_per_peer, cudaStream_t stream) {
+                     long long dst_heap_off, long long ready_off, long long done_off, long long scratch_off, int rank,
+                     int world, uint32_t epoch, int blocks_per_peer, cudaStream_t stream) {
   if (world > kMaxPeers) return cudaErrorInvalidValue;
   if (blocks_per_peer < 1) blocks_per_peer = 1;
   const int grid = world * blocks_per_peer;
   p2p_push_kernel<<<grid, kPushThreads, 0, stream>>>(static_cast<const uint8_t*>(src), plan, peer_table, dst_heap_off,
-                                                     ready_off, done_off, rank, world, epoch, blocks_per_peer);
+                                                     ready_off, done_off, scratch_off, rank, world, epoch, blocks_per_peer);
   return cudaGetLastError();
 }
 

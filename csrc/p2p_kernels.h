@@ -20,10 +20,11 @@ struct PushPlan {
 // Counters (uint32, inside the heap, zero-initialised, monotonically increasing):
 //   ready[W] at heap offset ready_off: ready[src] on rank d counts "d's receive region is free" credits that d
 //             granted to src.  done[W] at done_off: done[src] on rank d counts finished pushes of src into d.
+//   scratch[W] at scratch_off: LOCAL block-arrival counters used to elect the last block per destination.
 // `epoch` is the 1-based call number on this (ready, done) counter pair.
 cudaError_t p2p_push(const void* src, const PushPlan& plan, const unsigned long long* peer_table,
-                     long long dst_heap_off, long long ready_off, long long done_off, int rank, int world,
-                     uint32_t epoch, int blocks_per_peer, cudaStream_t stream);
+                     long long dst_heap_off, long long ready_off, long long done_off, long long scratch_off, int rank,
+                     int world, uint32_t epoch, int blocks_per_peer, cudaStream_t stream);
 
 // out[i] = sum_p peer_p[stage_off + slice_off + i]  for i in [0, n)   (one-shot pull-reduce; fp32 accumulate).
 // Callers bracket it with p2p_barrier so that all stages are written / may be overwritten.

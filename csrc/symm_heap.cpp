@@ -131,7 +131,8 @@ void register_symm_bindings(pybind11::module& m) {
   // src: any local CUDA tensor (bytes view); per-peer byte offsets/sizes as python lists.
   m.def("p2p_push", [](const at::Tensor& src, std::vector<int64_t> src_off, std::vector<int64_t> dst_off,
                        std::vector<int64_t> nbytes, int64_t peer_table, int64_t dst_heap_off, int64_t ready_off,
-                       int64_t done_off, int64_t rank, int64_t world, int64_t epoch, int64_t blocks_per_peer) {
+                       int64_t done_off, int64_t scratch_off, int64_t rank, int64_t world, int64_t epoch,
+                       int64_t blocks_per_peer) {
     TORCH_CHECK(src.is_cuda() && src.is_contiguous());
     TORCH_CHECK(world <= tb::kMaxPeers && (int64_t)src_off.size() == world && (int64_t)dst_off.size() == world &&
                 (int64_t)nbytes.size() == world);
@@ -139,7 +140,7 @@ void register_symm_bindings(pybind11::module& m) {
     tb::PushPlan plan{};
     for (int p = 0; p < world; ++p) { plan.src_off[p] = src_off[p]; plan.dst_off[p] = dst_off[p]; plan.bytes[p] = nbytes[p]; }
     TB_CHECK_CUDA(tb::p2p_push(src.data_ptr(), plan, reinterpret_cast<const unsigned long long*>(peer_table),
-                               dst_heap_off, ready_off, done_off, static_cast<int>(rank), static_cast<int>(world),
+                               dst_heap_off, ready_off, done_off, scratch_off, static_cast<int>(rank), static_cast<int>(world),
                                static_cast<uint32_t>(epoch), static_cast<int>(blocks_per_peer), cur_stream()));
   });
   m.def("p2p_reduce_slice", [](at::Tensor& out, int64_t peer_table, int64_t stage_off, int64_t slice_off_bytes,

@@ -70,6 +70,8 @@ class _BufferSet:
 
 
 class FusedEngine:
+    _serial = 0
+
     def __init__(self, layer, transport: 'p2p.P2PTransport', dtype: torch.dtype):
         ex = layer.experts
         self.t = transport
@@ -77,7 +79,8 @@ class FusedEngine:
         self.El, self.E = layer.num_local_experts, layer.num_global_experts
         self.M, self.H, self.Mo = layer.model_dim, ex.hidden_size, ex.output_dim
         self.dtype, self.es = dtype, torch.empty((), dtype=dtype).element_size()
-        self.tag = 'moe%x' % id(layer)
+        FusedEngine._serial += 1                 # same creation order on every rank -> same names and offsets
+        self.tag = 'moe%d' % FusedEngine._serial
         self.sets: Dict[int, List[_BufferSet]] = {}
         self.clock = 0
         self.side = torch.cuda.Stream()
@@ -140,9 +143,6 @@ class FusedEngine:
         return cg, bn, (-(-C // (128 * cg))) * (-(-N // bn))
 
 
-_ENGINES: Dict[int, Optional[FusedEngine]] = {}
-
-
 def engine_for(layer, x: torch.Tensor, crit, d: int):
     """Return a runnable fused engine for this call, or None when the generic path must be used."""
     if not _enabled() or not backend.use_tcgen05(x):
@@ -155,11 +155,11 @@ def engine_for(layer, x: torch.Tensor, crit, d: int):
         return None
     if ex.batched_fc1_w.dtype != x.dtype or (layer.model_dim % 8) or (ex.hidden_size % 8) or (ex.output_dim % 8):
         return None
-    key = id(layer)
-    if key not in _ENGINES:
+    eng = layer.__dict__.get('_fused_engine', False)
+    if eng is False:
         t = p2p.transport_for(layer.group)
-        _ENGINES[key] = FusedEngine(layer, t, x.dtype) if t is not None else None
-    eng = _ENGINES[key]
+        eng = FusedEngine(layer, t, x.dtype) if t is not None else None
+        layer.__dict__['_fused_engine'] = eng        # kept on the layer itself (id() values get recycled)
     if eng is None or eng.dtype != x.dtype:
         return None
     return _Runner(eng, d)

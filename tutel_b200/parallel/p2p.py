@@ -99,7 +99,8 @@ class P2PTransport:
         dist.barrier(group=group)
         self.peer_table = self.heap.peer_table_ptr()
         self._C = _C
-        # counter slots: slot s -> ready at 256*s, done at 256*s+64, barrier at 256*s+128 (uint32[16] each)
+        # counter slots: slot s -> ready at 256*s, done at 256*s+64, barrier at 256*s+128, local scratch at 256*s+192
+        # (uint32[16] each)
         self._epochs: Dict[int, int] = {}
         self._named: Dict[str, tuple] = {}
         self._next_slot = 2  # slot 0: generic push, slot 1: generic barrier/reduce
@@ -168,7 +169,8 @@ class P2PTransport:
     def push(self, src: torch.Tensor, src_off: List[int], dst_off: List[int], nbytes: List[int], dst_heap_off: int,
              slot: int = 0) -> None:
         self._C.p2p_push(src, src_off, dst_off, nbytes, self.peer_table, dst_heap_off, 256 * slot, 256 * slot + 64,
-                         self.rank, self.world, self._next_epoch(slot), self._blocks_per_peer(max(nbytes)))
+                         256 * slot + 192, self.rank, self.world, self._next_epoch(slot),
+                         self._blocks_per_peer(max(nbytes)))
 
     # ---- generic collectives (staging region; results are copied out so that callers may keep them) -------------
     def fits(self, nbytes: int) -> bool:
