@@ -155,11 +155,11 @@ def engine_for(layer, x: torch.Tensor, crit, d: int):
         return None
     if ex.batched_fc1_w.dtype != x.dtype or (layer.model_dim % 8) or (ex.hidden_size % 8) or (ex.output_dim % 8):
         return None
-    eng = layer.__dict__.get('_fused_engine', False)
+    eng = layer.__dict__.get('_tb_fused_state', False)
     if eng is False:
         t = p2p.transport_for(layer.group)
         eng = FusedEngine(layer, t, x.dtype) if t is not None else None
-        layer.__dict__['_fused_engine'] = eng        # kept on the layer itself (id() values get recycled)
+        layer.__dict__['_tb_fused_state'] = eng        # kept on the layer itself (id() values get recycled)
     if eng is None or eng.dtype != x.dtype:
         return None
     return _Runner(eng, d)

@@ -164,7 +164,7 @@ class P2PTransport:
             return 1
         if max_bytes <= (1 << 20):
             return 4
-        return max(1, min(32, 296 // self.world))
+        return max(8, min(74, 592 // self.world))     # ~4 CTAs per SM in total: enough bytes in flight for NVLink
 
     def push(self, src: torch.Tensor, src_off: List[int], dst_off: List[int], nbytes: List[int], dst_heap_off: int,
              slot: int = 0) -> None:
