@@ -297,9 +297,13 @@ def batch_all_gather_v(datas: Sequence[torch.Tensor], group=None):
         if t is not None:
             outputs.append(t.all_gather_v(d, sizes))
         else:
-            pieces = [torch.empty([n], dtype=d.dtype, device=d.device) for n in sizes]
-            dist.all_gather(pieces, d, group=group)
-            outputs.append(torch.cat(pieces))
+            # equal-size gather of padded pieces (Gloo and older NCCL builds reject ragged lists), then trim
+            width = max(sizes)
+            padded = torch.zeros([width], dtype=d.dtype, device=d.device)
+            padded[: d.numel()] = d
+            pieces = [torch.empty([width], dtype=d.dtype, device=d.device) for _ in sizes]
+            dist.all_gather(pieces, padded, group=group)
+            outputs.append(torch.cat([p[:n] for p, n in zip(pieces, sizes)]))
     return outputs, output_sizes
 
 

@@ -201,9 +201,12 @@ class P2PTransport:
         es = x.element_size()
         total = sum(sizes) * es
         if not self.fits(total):
-            pieces = [torch.empty([n], dtype=x.dtype, device=x.device) for n in sizes]
-            dist.all_gather(pieces, x, group=self.group)
-            return torch.cat(pieces)
+            width = max(sizes)
+            padded = torch.zeros([width], dtype=x.dtype, device=x.device)
+            padded[: x.numel()] = x
+            pieces = [torch.empty([width], dtype=x.dtype, device=x.device) for _ in sizes]
+            dist.all_gather(pieces, padded, group=self.group)
+            return torch.cat([p[:n] for p, n in zip(pieces, sizes)])
         my_off = sum(sizes[: self.rank]) * es
         n = sizes[self.rank] * es
         self.push(x, [0] * self.world, [my_off] * self.world, [n] * self.world, self.stage_off)
