@@ -140,7 +140,7 @@ at::Tensor build_slot_map(const at::Tensor& idx, const at::Tensor& loc, int64_t 
 // x [S, M]; gates float [k, S] or None; slot_src int [E*C]; out [E*C, M] (ignored rows live in dst_ptr_table).
 void encode_rows(const at::Tensor& x, const c10::optional<at::Tensor>& gates, const at::Tensor& slot_src,
                  at::Tensor& out, int64_t k, int64_t E, int64_t C, int64_t dst_ptr_table, int64_t signal_ptr_table,
-                 int64_t signal_rows, int64_t rot_chunks, int64_t signal_value) {
+                 int64_t signal_rows, int64_t rot_chunks, int64_t signal_value, int64_t chunk_counters) {
   TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous() && slot_src.is_cuda() && slot_src.is_contiguous());
   TORCH_CHECK(slot_src.scalar_type() == at::kInt && slot_src.numel() == E * C);
   const c10::cuda::CUDAGuard guard(x.device());
@@ -155,7 +155,7 @@ void encode_rows(const at::Tensor& x, const c10::optional<at::Tensor>& gates, co
   TB_CHECK_CUDA(tb::encode_rows(x.data_ptr(), g, slot_src.data_ptr<int>(), out.data_ptr(),
                                 reinterpret_cast<const unsigned long long*>(dst_ptr_table),
                                 reinterpret_cast<const unsigned long long*>(signal_ptr_table),
-                                static_cast<int>(signal_rows), static_cast<int>(x.size(0)), static_cast<int>(E),
+                                reinterpret_cast<unsigned int*>(chunk_counters), static_cast<int>(signal_rows), static_cast<int>(x.size(0)), static_cast<int>(E),
                                 static_cast<int>(k), static_cast<int>(C), static_cast<int>(x.size(1)), elem_type_of(x),
                                 static_cast<int>(rot_chunks), static_cast<int>(signal_value), cur_stream()));
 }

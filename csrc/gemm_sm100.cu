@@ -205,6 +205,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // =============================== TMA producer ===============================
     int s = 0;
     uint32_t ph = 0;
+    int seen_group = -1;
+    unsigned long long seen_mask = 0ull;
     for (long long t = tile_first; t < args.num_tiles; t += tile_step) {
       TileCoord tc = decode_tile<kBand>(t, args.tiles_m, args.tiles_n);
       tc.g = rotate_group(tc.g, args.group_rot, args.group_mod);
@@ -213,16 +215,24 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * C::BN_CTA;
       const int gb = tc.g / args.b_group_div;
       if (args.wait_flags != nullptr) {
-        // Dispatch fusion: rows of this tile are pushed by peer GPUs; wait for their release-counters.
-        if (lane == 0) {
-          const int f0 = (tc.m_blk * C::BM) / args.wait_rows_per_flag;
-          int f1 = (min(tc.m_blk * C::BM + C::BM, args.M) - 1) / args.wait_rows_per_flag;
-          for (int f = f0; f <= f1; ++f)
-            ptx::wait_flag_ge_sys(args.wait_flags + static_cast<long long>(tc.g) * args.wait_flags_per_group + f,
-                                  args.wait_target);
-          ptx::fence_proxy_async_global();  // order the upcoming async-proxy (TMA) reads after the acquire
+        // Dispatch fusion: rows of this tile are pushed by peer GPUs; acquire their release flags - once per
+        // (group, flag): consecutive tiles of a group share flags, so remember which ones were already seen.
+        if (tc.g != seen_group) { seen_group = tc.g; seen_mask = 0ull; }
+        const int f0 = (tc.m_blk * C::BM) / args.wait_rows_per_flag;
+        const int f1 = (min(tc.m_blk * C::BM + C::BM, args.M) - 1) / args.wait_rows_per_flag;
+        unsigned long long need = 0ull;
+        for (int f = f0; f <= f1; ++f) need |= 1ull << (f & 63);
+        if ((seen_mask & need) != need) {
+          if (lane == 0) {
+            for (int f = f0; f <= f1; ++f)
+              if (!((seen_mask >> (f & 63)) & 1ull))
+                ptx::wait_flag_ge_sys(args.wait_flags + static_cast<long long>(tc.g) * args.wait_flags_per_group + f,
+                                      args.wait_target);
+            ptx::fence_proxy_async_global();  // order the upcoming async-proxy (TMA) reads after the acquire
+          }
+          __syncwarp();
+          seen_mask |= need;
         }
-        __syncwarp();
       }
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(empty_bar(s), ph ^ 1u);

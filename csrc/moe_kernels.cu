@@ -199,17 +199,21 @@ template <typename T, bool VEC>
 __global__ void __launch_bounds__(kEncThreads)
 encode_rows_kernel(const T* __restrict__ x, const float* __restrict__ gates, const int* __restrict__ slot_src,
                    T* __restrict__ out, const unsigned long long* __restrict__ dst_ptr_table,
-                   const unsigned long long* __restrict__ signal_ptr_table, int chunk_rows, int S, int E, int k, int C,
-                   int M, int rot_chunks, uint32_t signal_value) {
+                   const unsigned long long* __restrict__ signal_ptr_table, unsigned int* __restrict__ chunk_counters,
+                   int chunk_rows, int unit_rows, int S, int E, int k, int C, int M, int rot_units,
+                   uint32_t signal_value) {
+  // Work unit = `unit_rows` consecutive slots of one expert (one warp per row).  Many blocks cooperate on one flag
+  // chunk (`chunk_rows` rows); the block that finishes the chunk's last unit publishes the flag.
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int units_per_expert = (C + unit_rows - 1) / unit_rows;
   const int chunks_per_expert = (C + chunk_rows - 1) / chunk_rows;
-  const long long total_chunks = static_cast<long long>(E) * chunks_per_expert;
-  for (long long ci = blockIdx.x; ci < total_chunks; ci += gridDim.x) {
-    const long long c = (ci + rot_chunks) % total_chunks;
-    const int e = static_cast<int>(c / chunks_per_expert);
-    const int r0 = static_cast<int>(c - static_cast<long long>(e) * chunks_per_expert) * chunk_rows;
-    const int r1 = min(r0 + chunk_rows, C);
+  const long long total_units = static_cast<long long>(E) * units_per_expert;
+  for (long long ui = blockIdx.x; ui < total_units; ui += gridDim.x) {
+    const long long u = (ui + rot_units) % total_units;
+    const int e = static_cast<int>(u / units_per_expert);
+    const int r0 = static_cast<int>(u - static_cast<long long>(e) * units_per_expert) * unit_rows;
+    const int r1 = min(r0 + unit_rows, C);
     T* dst_e = dst_ptr_table != nullptr ? reinterpret_cast<T*>(dst_ptr_table[e])
                                         : out + static_cast<long long>(e) * C * M;
     for (int r = r0 + warp; r < r1; r += kEncWarps) {
@@ -233,22 +237,22 @@ encode_rows_kernel(const T* __restrict__ x, const float* __restrict__ gates, con
         const uint4* sv = reinterpret_cast<const uint4*>(srow);
         uint4* dv = reinterpret_cast<uint4*>(drow);
         int v = lane;
-        for (; v + 96 < nv; v += 128) {
-          uint4 a[4];
+        for (; v + 224 < nv; v += 256) {   // 8 x 16 B in flight per lane
+          uint4 a[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) a[u] = ptx::ld_nc_v4(sv + v + 32 * u);
+          for (int q = 0; q < 8; ++q) a[q] = ptx::ld_nc_v4(sv + v + 32 * q);
           if (gates != nullptr) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int q = 0; q < 8; ++q) {
               float f[Vec<T>::N];
-              Vec<T>::unpack(a[u], f);
+              Vec<T>::unpack(a[q], f);
 #pragma unroll
-              for (int q = 0; q < Vec<T>::N; ++q) f[q] *= g;
-              a[u] = Vec<T>::pack(f);
+              for (int i = 0; i < Vec<T>::N; ++i) f[i] *= g;
+              a[q] = Vec<T>::pack(f);
             }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) ptx::st_na_v4(dv + v + 32 * u, a[u]);
+          for (int q = 0; q < 8; ++q) ptx::st_na_v4(dv + v + 32 * q, a[q]);
         }
         for (; v < nv; v += 32) {
           uint4 a = ptx::ld_nc_v4(sv + v);
@@ -256,7 +260,7 @@ encode_rows_kernel(const T* __restrict__ x, const float* __restrict__ gates, con
             float f[Vec<T>::N];
             Vec<T>::unpack(a, f);
 #pragma unroll
-            for (int q = 0; q < Vec<T>::N; ++q) f[q] *= g;
+            for (int i = 0; i < Vec<T>::N; ++i) f[i] *= g;
             a = Vec<T>::pack(f);
           }
           ptx::st_na_v4(dv + v, a);
@@ -266,12 +270,22 @@ encode_rows_kernel(const T* __restrict__ x, const float* __restrict__ gates, con
       }
     }
     if (signal_ptr_table != nullptr) {
-      __syncthreads();  // every warp's stores of this chunk are issued and ordered before the release below
+      __syncthreads();  // every warp's stores of this unit are issued and ordered before the counter update below
       if (threadIdx.x == 0) {
-        ptx::fence_acq_rel_sys();
-        uint32_t* flag = reinterpret_cast<uint32_t*>(signal_ptr_table[e]) + r0 / chunk_rows;
-        if (signal_value != 0u) ptx::st_release_sys(flag, signal_value);
-        else ptx::red_add_release_sys(flag, 1u);
+        const int ci = r0 / chunk_rows;
+        const int chunk_begin = ci * chunk_rows;
+        const int chunk_end = min(chunk_begin + chunk_rows, C);
+        const unsigned units_in_chunk = static_cast<unsigned>((chunk_end - chunk_begin + unit_rows - 1) / unit_rows);
+        unsigned int* cnt = chunk_counters + static_cast<long long>(e) * chunks_per_expert + ci;
+        unsigned prev;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(cnt) : "memory");
+        if (prev == units_in_chunk - 1u) {
+          *cnt = 0u;  // re-arm for the next launch (stream ordered)
+          uint32_t* flag = reinterpret_cast<uint32_t*>(signal_ptr_table[e]) + ci;
+          ptx::fence_acq_rel_sys();
+          if (signal_value != 0u) ptx::st_release_sys(flag, signal_value);
+          else ptx::red_add_release_sys(flag, 1u);
+        }
       }
     }
   }
@@ -504,36 +518,41 @@ cudaError_t build_slot_map(const int* idx, const int* loc, int* slot_src, int S,
 template <typename T>
 static cudaError_t encode_rows_t(const void* x, const void* gates, const int* slot_src, void* out,
                                  const unsigned long long* dst_ptr_table, const unsigned long long* signal_ptr_table,
-                                 int signal_rows, int S, int E, int k, int C, int M, int rot, int signal_value, int max_blocks,
-                                 cudaStream_t stream) {
+                                 unsigned int* chunk_counters, int signal_rows, int S, int E, int k, int C, int M,
+                                 int rot_chunks, int signal_value, cudaStream_t stream) {
   if (E <= 0 || C <= 0 || M <= 0) return cudaSuccess;
-  const int chunk_rows = signal_rows > 0 ? signal_rows : 16;
-  const long long chunks = static_cast<long long>(E) * ((C + chunk_rows - 1) / chunk_rows);
-  int grid = static_cast<int>(chunks < 4LL * num_sms() ? chunks : 4LL * num_sms());
-  if (max_blocks > 0 && grid > max_blocks) grid = max_blocks;
+  const int unit_rows = 16;
+  int chunk_rows = signal_rows > 0 ? signal_rows : unit_rows;
+  chunk_rows = (chunk_rows + unit_rows - 1) / unit_rows * unit_rows;
+  if (signal_ptr_table != nullptr && chunk_counters == nullptr) return cudaErrorInvalidValue;
+  const long long units = static_cast<long long>(E) * ((C + unit_rows - 1) / unit_rows);
+  // remote pushes share the SMs with the concurrently running expert GEMM: 2 blocks per SM are plenty for NVLink
+  const long long cap = (dst_ptr_table != nullptr ? 2LL : 4LL) * num_sms();
+  const int grid = static_cast<int>(units < cap ? units : cap);
+  const int rot_units = rot_chunks * (chunk_rows / unit_rows);
   const bool vec = (M % Vec<T>::N == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                    (dst_ptr_table != nullptr || (reinterpret_cast<uintptr_t>(out) & 15) == 0);
   if (vec)
     encode_rows_kernel<T, true><<<grid, kEncThreads, 0, stream>>>(
         static_cast<const T*>(x), static_cast<const float*>(gates), slot_src, static_cast<T*>(out), dst_ptr_table,
-        signal_ptr_table, chunk_rows, S, E, k, C, M, rot, static_cast<uint32_t>(signal_value));
+        signal_ptr_table, chunk_counters, chunk_rows, unit_rows, S, E, k, C, M, rot_units,
+        static_cast<uint32_t>(signal_value));
   else
     encode_rows_kernel<T, false><<<grid, kEncThreads, 0, stream>>>(
         static_cast<const T*>(x), static_cast<const float*>(gates), slot_src, static_cast<T*>(out), dst_ptr_table,
-        signal_ptr_table, chunk_rows, S, E, k, C, M, rot, static_cast<uint32_t>(signal_value));
+        signal_ptr_table, chunk_counters, chunk_rows, unit_rows, S, E, k, C, M, rot_units,
+        static_cast<uint32_t>(signal_value));
   return cudaGetLastError();
 }
 
 cudaError_t encode_rows(const void* x, const void* gates, const int* slot_src, void* out,
                         const unsigned long long* dst_ptr_table, const unsigned long long* signal_ptr_table,
-                        int signal_rows, int S, int E, int k, int C, int M, int elem_type, int rot_chunks,
-                        int signal_value, cudaStream_t stream) {
-  // remote pushes leave most SMs to the concurrently running expert GEMM
-  const int max_blocks = dst_ptr_table != nullptr ? 96 : 0;
+                        unsigned int* chunk_counters, int signal_rows, int S, int E, int k, int C, int M, int elem_type,
+                        int rot_chunks, int signal_value, cudaStream_t stream) {
   switch (elem_type) {
-    case ET_F32: return encode_rows_t<float>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, signal_rows, S, E, k, C, M, rot_chunks, signal_value, max_blocks, stream);
-    case ET_F16: return encode_rows_t<__half>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, signal_rows, S, E, k, C, M, rot_chunks, signal_value, max_blocks, stream);
-    case ET_BF16: return encode_rows_t<__nv_bfloat16>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, signal_rows, S, E, k, C, M, rot_chunks, signal_value, max_blocks, stream);
+    case ET_F32: return encode_rows_t<float>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, chunk_counters, signal_rows, S, E, k, C, M, rot_chunks, signal_value, stream);
+    case ET_F16: return encode_rows_t<__half>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, chunk_counters, signal_rows, S, E, k, C, M, rot_chunks, signal_value, stream);
+    case ET_BF16: return encode_rows_t<__nv_bfloat16>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, chunk_counters, signal_rows, S, E, k, C, M, rot_chunks, signal_value, stream);
   }
   return cudaErrorInvalidValue;
 }

@@ -24,11 +24,13 @@ cudaError_t build_slot_map(const int* idx, const int* loc, int* slot_src, int S,
 // fusion); when null the block of expert e is out + e*C*M.
 // signal_ptr_table/signal_rows (optional): after rows [r0, r0+signal_rows) of expert e are stored, the uint32
 // counter at signal_ptr_table[e] + (r0/signal_rows) is set to `signal_value` with st.release.sys (each chunk has a
-// single writer, so the epoch number itself is published; 0 = increment instead).
+// single publisher - the block that finishes the chunk's last 16-row unit, elected through `chunk_counters`
+// (uint32[E * ceil(C/signal_rows)], zero-initialised, self-resetting) - so the epoch number itself is published;
+// 0 = increment instead).
 cudaError_t encode_rows(const void* x, const void* gates, const int* slot_src, void* out,
                         const unsigned long long* dst_ptr_table, const unsigned long long* signal_ptr_table,
-                        int signal_rows, int S, int E, int k, int C, int M, int elem_type, int rot_chunks,
-                        int signal_value, cudaStream_t stream);
+                        unsigned int* chunk_counters, int signal_rows, int S, int E, int k, int C, int M, int elem_type,
+                        int rot_chunks, int signal_value, cudaStream_t stream);
 
 // out[s, :] = sum_j w_j * buf[idx_j[s]*C + loc_j[s], :]  (choices with loc >= C or idx < 0 contribute 0).
 // wait_flags (optional): uint32[E] counters that must reach wait_target (acquire.sys) before expert e's rows

@@ -79,7 +79,7 @@ def raw_encode(x: torch.Tensor, gates: Optional[torch.Tensor], plan: DispatchPla
         out = torch.empty([plan.E * plan.C, M], dtype=x.dtype, device=x.device)
         g = None if gates is None else gates.to(torch.float32).contiguous()
         backend.count_launch()
-        backend.require_ext().encode_rows(x, g, plan.slot_src, out, plan.k, plan.E, plan.C, 0, 0, 0, 0, 0)
+        backend.require_ext().encode_rows(x, g, plan.slot_src, out, plan.k, plan.E, plan.C, 0, 0, 0, 0, 0, 0)
         return out
     if _cpu_native(x):
         g = None if gates is None else gates.to(x.dtype).contiguous()

@@ -84,6 +84,7 @@ class FusedEngine:
         self.sets: Dict[int, List[_BufferSet]] = {}
         self.clock = 0
         self.side = torch.cuda.Stream()
+        self.chunk_counters = torch.zeros([self.E * _FLAGS_PER_SEG], dtype=torch.int32, device='cuda')
         self.disabled_for: set = set()
 
     # ---- buffer ring ------------------------------------------------------------------------------------------
@@ -132,8 +133,10 @@ class FusedEngine:
         return self._table(s, ('cd', data_off, width), dst), self._table(s, ('cs', flag_off), sig)
 
     def chunk_rows(self, C: int, d: int) -> int:
-        rows = max(256, -(-C // max(d, 1)))
-        rows = max(rows, -(-C // _FLAGS_PER_SEG))
+        """Rows per arrival flag.  One MMA tile (256 rows) is the finest useful granularity; `d` (the layer's
+        a2a_ffn_overlap_degree) can only make it finer than the default C/8, never coarser than C."""
+        rows = -(-C // max(d, 8))
+        rows = max(256, rows, -(-C // _FLAGS_PER_SEG))
         return (rows + 255) // 256 * 256
 
     @staticmethod
@@ -194,7 +197,7 @@ def _push(eng: FusedEngine, bufs: _BufferSet, plan: DispatchPlan, src: torch.Ten
     with torch.cuda.stream(eng.side):
         backend.count_launch()
         C_ext.encode_rows(src, gates_f32, plan.slot_src, src, plan.k, plan.E, plan.C, dst_tab, sig_tab, chunk,
-                          eng.rank * eng.El * chunks_per_expert, bufs.epoch)
+                          eng.rank * eng.El * chunks_per_expert, bufs.epoch, eng.chunk_counters.data_ptr())
         ev = torch.cuda.Event()
         ev.record(eng.side)
     src.record_stream(eng.side)
@@ -278,13 +281,16 @@ class _FusedMoE(torch.autograd.Function):
                         wait_flags=base + bufs.b_disp, wait_rows_per_flag=chunk, wait_flags_per_group=_FLAGS_PER_SEG,
                         wait_target=bufs.epoch, group_rot=rank, group_mod=-W)
 
-        # (e) dX_e = dh @ W1, epilogue pushes into the source GPUs' dX_comb
-        cgx, bnx, tilesx = eng.tile_counts(C, M)
-        d_tab, s_tab = eng.combine_tables(bufs, bufs.dx_comb, bufs.b_comb, M)
+        # (e) dX_e = dh @ W1, epilogue pushes into the source GPUs' dX_comb.  Collective decision: every rank
+        #     must run it if any rank needs input gradients - the flag is part of the saved context (same program).
+        need_dx = ctx.needs_input_grad[5] or (not is_postscore and ctx.needs_input_grad[6])
         dx_comb = t.view(bufs.dx_comb, [E, C, M], eng.dtype)
-        G.raw_gemm(dh, w1, b_mn=True, b_group_div=W, out=dx_comb, cta_group=cgx, block_n=bnx, d_ptr_table=d_tab,
-                   signal_ptr_table=s_tab, group_rot=rank, group_mod=-W)
-        bufs.comb_total[1] += tilesx
+        if need_dx:
+            cgx, bnx, tilesx = eng.tile_counts(C, M)
+            d_tab, s_tab = eng.combine_tables(bufs, bufs.dx_comb, bufs.b_comb, M)
+            G.raw_gemm(dh, w1, b_mn=True, b_group_div=W, out=dx_comb, cta_group=cgx, block_n=bnx, d_ptr_table=d_tab,
+                       signal_ptr_table=s_tab, group_rot=rank, group_mod=-W)
+            bufs.comb_total[1] += tilesx
 
         # (d, f) weight gradients over all W*C received rows of each local expert
         act_e, dh_e = act.view(El, W * C, H), dh.view(El, W * C, H)
@@ -296,7 +302,7 @@ class _FusedMoE(torch.autograd.Function):
 
         # (g) combine the input gradients (encode.bwd == decode of the gradient buffer)
         dx = None
-        if ctx.needs_input_grad[5] or not is_postscore:
+        if need_dx:
             backend.count_launch()
             dx = C_ext.decode_rows(dx_comb.view(E * C, M), None if is_postscore else gates_f32, plan.idx_ks, plan.loc_ks,
                                    E, C, base + bufs.b_comb, bufs.comb_total[1])
