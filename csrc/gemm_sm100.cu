@@ -25,6 +25,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "ptx.cuh"
@@ -58,6 +59,7 @@ struct GemmArgs {
   int wait_rows_per_flag, wait_flags_per_group;
   uint32_t wait_target;
   const unsigned long long* signal_ptr_table;
+  int staged_store;  // 16-bit outputs: stage rows in smem and write them with cp.async.bulk (full 64 B segments)
   int group_rot, group_mod;  // tile order visits group (g/mod)*mod + (g%mod + rot)%mod  (own-rank segment first)
 };
 
@@ -76,7 +78,10 @@ struct Cfg {
   static constexpr int A_BYTES = BM_CTA * kSwizzleBytes;
   static constexpr int B_BYTES = BN_CTA * kSwizzleBytes;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int AUX_BYTES = 1024 /*align slack*/ + 512 /*barriers + tmem ptr*/;
+  static constexpr int EPI_ROW_BYTES = 80;                       // 64 B of payload + 16 B pad (bank-conflict free)
+  static constexpr int EPI_SLOT_BYTES = 32 * EPI_ROW_BYTES;      // one warp, one 32-column chunk
+  static constexpr int EPI_BYTES = 4 * 2 * EPI_SLOT_BYTES;       // 4 epilogue warps, double buffered
+  static constexpr int AUX_BYTES = 1024 /*align slack*/ + 512 /*barriers + tmem ptr*/ + EPI_BYTES;
   static constexpr int STAGES_RAW = (kSmemLimit - AUX_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES;
@@ -170,6 +175,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  const uint32_t epi_base = bar_base + 512u;  // 16-byte aligned staging for the epilogue's row-wise bulk stores
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
@@ -335,6 +341,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc_ph = 0;
     const bool out16 = (args.out_dtype != DT_FP32);
     const bool out_bf16 = (args.out_dtype == DT_BF16);
+    const bool staged = out16 && args.staged_store != 0;
     for (long long t = tile_first; t < args.num_tiles; t += tile_step) {
       TileCoord tc = decode_tile<kBand>(t, args.tiles_m, args.tiles_n);
       tc.g = rotate_group(tc.g, args.group_rot, args.group_mod);
@@ -423,7 +430,25 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
 
-        if (row_ok) {
+        if (staged) {
+          // registers -> padded smem row (this thread's own) -> one asynchronous bulk store of the row segment
+          const uint32_t slot = epi_base + static_cast<uint32_t>(ew * 2 + (c & 1)) * C::EPI_SLOT_BYTES +
+                                static_cast<uint32_t>(lane) * C::EPI_ROW_BYTES;
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the bulk store that used this slot has read it
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t o0 = pack2(v[q * 8 + 0], v[q * 8 + 1], out_bf16), o1 = pack2(v[q * 8 + 2], v[q * 8 + 3], out_bf16);
+            const uint32_t o2 = pack2(v[q * 8 + 4], v[q * 8 + 5], out_bf16), o3 = pack2(v[q * 8 + 6], v[q * 8 + 7], out_bf16);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + q * 16), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
+                         : "memory");
+          }
+          ptx::fence_proxy_async_smem();
+          if (row_ok)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(d_row + n * 2), "r"(slot),
+                         "r"(static_cast<uint32_t>(ncols * 2))
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        } else if (row_ok) {
           if (out16) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -456,6 +481,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       if (args.signal_ptr_table != nullptr) {
         // Combine fusion: all 128 epilogue threads' (possibly remote) stores -> one release.sys counter bump.
+        if (staged) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this thread's bulk stores are complete
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (ew == 0 && lane == 0) {
           ptx::fence_acq_rel_sys();
@@ -464,6 +490,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
     }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // staging smem must outlive the last bulk reads
   }
 
   // ---- teardown ----
@@ -618,6 +645,14 @@ cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const c
   a.wait_flags = p.wait_flags; a.wait_rows_per_flag = p.wait_rows_per_flag > 0 ? p.wait_rows_per_flag : bm;
   a.wait_flags_per_group = p.wait_flags_per_group; a.wait_target = p.wait_target;
   a.signal_ptr_table = p.signal_ptr_table;
+  {
+    static int staged_default = -1;
+    if (staged_default < 0) {
+      const char* e = getenv("TUTEL_B200_EPI");
+      staged_default = (e != nullptr && (e[0] == 'd' || e[0] == '0')) ? 0 : 1;   // "direct" / "0" disables staging
+    }
+    a.staged_store = staged_default;
+  }
   a.group_rot = p.group_rot; a.group_mod = p.group_mod;
 
   CUtensorMap ta, tb_;
