@@ -80,8 +80,9 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, bool a_mn, bo
     p.bias_group_stride = bias->stride(0);
   }
   if (aux.has_value() && aux->defined()) {
-    TORCH_CHECK(aux->is_cuda() && aux->scalar_type() == d.scalar_type() && aux->dim() == 3 && aux->stride(2) == 1,
-                "tutel_b200.gemm: aux must be [G, M, N] of the output dtype");
+    TORCH_CHECK(aux->is_cuda() && aux->scalar_type() == d.scalar_type() && aux->dim() == 3 && aux->stride(2) == 1 &&
+                    aux->element_size() == 2,
+                "tutel_b200.gemm: aux must be a 16-bit [G, M, N] tensor of the output dtype");
     p.aux = aux->data_ptr();
     p.ld_aux = aux->stride(1);
     p.aux_group_stride = aux->stride(0);
@@ -210,6 +211,30 @@ std::vector<at::Tensor> gate_topk_forward(const at::Tensor& logits, int64_t k) {
   return {scores, idx, top, me, ce};
 }
 
+at::Tensor skinny_gemm(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias,
+                       const c10::optional<at::Tensor>& counts, bool w_is_kn, bool relu) {
+  TORCH_CHECK(x.is_cuda() && w.is_cuda() && x.dim() == 3 && w.dim() == 3 && x.is_contiguous() && w.is_contiguous());
+  TORCH_CHECK(x.scalar_type() == w.scalar_type() && x.size(0) == w.size(0));
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int G = static_cast<int>(x.size(0)), R = static_cast<int>(x.size(1)), K = static_cast<int>(x.size(2));
+  const int N = static_cast<int>(w_is_kn ? w.size(2) : w.size(1));
+  TORCH_CHECK((w_is_kn ? w.size(1) : w.size(2)) == K, "skinny_gemm: K mismatch");
+  at::Tensor y = at::zeros({G, R, N}, x.options());
+  const void* b = nullptr;
+  if (bias.has_value() && bias->defined()) {
+    TORCH_CHECK(bias->is_cuda() && bias->is_contiguous() && bias->scalar_type() == x.scalar_type() && bias->numel() == static_cast<int64_t>(G) * N);
+    b = bias->data_ptr();
+  }
+  const int* c = nullptr;
+  if (counts.has_value() && counts->defined()) {
+    TORCH_CHECK(counts->is_cuda() && counts->scalar_type() == at::kInt && counts->numel() >= G);
+    c = counts->data_ptr<int>();
+  }
+  TB_CHECK_CUDA(tb::skinny_grouped_gemm(x.data_ptr(), w.data_ptr(), b, y.data_ptr(), c, G, R, N, K, w_is_kn, relu,
+                                        elem_type_of(x), cur_stream()));
+  return y;
+}
+
 }  // namespace
 
 void register_symm_bindings(pybind11::module& m);  // symm_heap.cpp / p2p bindings
@@ -226,6 +251,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("decode_rows", &decode_rows);
   m.def("gate_grad", &gate_grad);
   m.def("gate_topk_forward", &gate_topk_forward);
+  m.def("skinny_gemm", &skinny_gemm);
   register_symm_bindings(m);
   register_cpu_bindings(m);
   register_jit_bindings(m);

@@ -48,4 +48,10 @@ cudaError_t gate_grad(const void* a, const void* buf, const int* idx, const int*
 cudaError_t gate_topk_forward(const float* logits, float* scores, int* idx, float* topk_scores, float* me_partial,
                               int* ce_partial, int S, int E, int k, cudaStream_t stream);
 
+// Dropless / decoder inference: y[g, r, :] = act(x[g, r, :] @ W[g] + bias[g]) for r < counts[g] (device counts, no
+// host sync); x [G, rows_cap, K], y [G, rows_cap, N], W [G, N, K] or (w_is_kn) [G, K, N].  Rows past the count are
+// left untouched.  (csrc/skinny_gemm.cu)
+cudaError_t skinny_grouped_gemm(const void* x, const void* w, const void* bias, void* y, const int* counts, int G,
+                                int rows_cap, int N, int K, bool w_is_kn, bool relu, int elem_type, cudaStream_t stream);
+
 }  // namespace tb

@@ -125,6 +125,13 @@ class FusedExpertsNetwork(torch.nn.Module):
         lead = x.shape
         if x.dim() > 3:
             x = x.reshape(x.size(0), x.size(1), -1)
+        if row_counts is not None and G.can_use_skinny(x, w1):
+            # dropless decoder inference: a few tokens per expert -> stream only the active experts' weights once
+            relu = self._act_kind == 'relu'
+            y = G.skinny_linear(x, w1, b1, 'nk', row_counts, relu=relu)
+            if not relu:
+                y = self.activation_fn(y)
+            return G.skinny_linear(y, w2, b2, 'kn', row_counts)
         if self._act_kind == 'relu' and G.can_use_tcgen05(x, w1) and G.can_use_tcgen05(x, w2):
             y = G.fused_relu_ffn(x, w1, b1, w2, b2, row_counts)
         else:

@@ -197,3 +197,16 @@ def classify_activation(fn) -> Optional[str]:
     except Exception:  # noqa
         pass
     return kind or None
+
+
+def can_use_skinny(x: torch.Tensor, w: torch.Tensor) -> bool:
+    """Few rows per expert (decoder inference / dropless routing) on CUDA, no autograd: use the weight-streaming kernel."""
+    return (x.is_cuda and x.dim() == 3 and x.size(1) <= 64 and x.dtype == w.dtype and not torch.is_grad_enabled() and
+            x.dtype in (torch.float32, torch.float16, torch.bfloat16) and backend.has_cuda_ext())
+
+
+def skinny_linear(x, w, bias, w_layout, row_counts, relu=False):
+    """y[g, r] = act(x[g, r] @ W[g] + b[g]) for r < row_counts[g] (csrc/skinny_gemm.cu); other rows are zero."""
+    backend.count_launch()
+    b = None if bias is None else bias.reshape(w.size(0), -1).contiguous()
+    return backend.require_ext().skinny_gemm(x.contiguous(), w.contiguous(), b, row_counts, w_layout == 'kn', relu)
