@@ -42,6 +42,8 @@ def gemm_cases():
     cases.append(dict(kind='gemm', M=14336, N=4096, K=16384, G=1, a_mn=True, b_mn=True, cg=2, bn=256, perf=True))
     cases.append(dict(kind='gemm', M=8192, N=8192, K=8192, G=1, a_mn=False, b_mn=False, cg=2, bn=256, perf=True))
     cases.append(dict(kind='gemm', M=8192, N=8192, K=8192, G=1, a_mn=False, b_mn=False, cg=1, bn=256, perf=True))
+    cases.append(dict(kind='fp8', M=16384, N=14336, K=4096, G=1, cg=2))
+    cases.append(dict(kind='fp8', M=16384, N=4096, K=14336, G=1, cg=2))
     return cases
 
 
@@ -251,7 +253,37 @@ def run_jit(c):
     return dict(ok=bool(torch.allclose(y, x * 3 + 1, rtol=1e-5, atol=1e-5)), y=y[:4].tolist(), x=x[:4].tolist())
 
 
-RUNNERS = dict(gemm=run_gemm, route=run_route, dispatch=run_dispatch, gate=run_gate, jit=run_jit)
+def run_fp8(c):
+    import torch
+    from tutel_b200.ops import gemm as G
+    M, N, K, Gn = c['M'], c['N'], c['K'], c['G']
+    a = (torch.randn(Gn, M, K, device='cuda') * 0.5).bfloat16()
+    b = (torch.randn(Gn, N, K, device='cuda') * 0.5).bfloat16()
+    aq, sa = G.quantize_rows(a)
+    bq, sb = G.quantize_rows(b)
+    d = torch.empty(Gn, M, N, device='cuda', dtype=torch.bfloat16)
+    call = lambda: G.raw_gemm(aq, bq, out=d, scale_a=sa, scale_b=sb, cta_group=c['cg'])
+    call()
+    ref = torch.matmul(a[:, :512].float(), b.float().transpose(1, 2))
+    rel = ((d[:, :512].float() - ref).norm() / ref.norm()).item()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record(); torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        return sorted(ts)[5]
+    t = timeit(call)
+    tq = timeit(lambda: G.quantize_rows(a))
+    return dict(ok=rel < 0.06, rel_err=rel, ms_median=t, tflops_median=2.0 * M * N * K * Gn / t * 1e-9, quantize_rows_ms=tq,
+                quantize_GBps=(a.numel() * 3) / tq * 1e-6)
+
+
+RUNNERS = dict(fp8=run_fp8, gemm=run_gemm, route=run_route, dispatch=run_dispatch, gate=run_gate, jit=run_jit)
 
 
 def main():

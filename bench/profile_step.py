@@ -65,4 +65,17 @@ if rank == 0:
         f.write('# total kernel time per step: %.1f us\n' % sum(r[0] for r in rows))
         for t, c, k in rows:
             f.write('%10.1f %6.1f  %s\n' % (t, c, k[:160]))
-    print(open(args.out).read()[:6000])
+    # timeline of the last profiled step: start offset (us), duration (us), stream, kernel
+    evs = [e for e in prof.events() if e.device_type.name == 'CUDA' and e.time_range.end > e.time_range.start]
+    evs.sort(key=lambda e: e.time_range.start)
+    if evs:
+        t_end = evs[-1].time_range.end
+        span = (t_end - evs[0].time_range.start) / args.steps
+        last = [e for e in evs if e.time_range.start >= t_end - span * 1.02 and not e.name.startswith('Optimizer')]
+        t0 = last[0].time_range.start
+        with open(args.out.replace('.txt', '_timeline.txt'), 'w') as f:
+            f.write('# start_us dur_us stream kernel (last profiled step, rank 0)\n')
+            for e in last:
+                f.write('%9.1f %8.1f %3s  %s\n' % (e.time_range.start - t0, e.time_range.end - e.time_range.start,
+                                                   getattr(e, 'device_index', ''), e.name[:110]))
+    print(open(args.out).read()[:3000])

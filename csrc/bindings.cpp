@@ -50,7 +50,8 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, bool a_mn, bo
           const c10::optional<at::Tensor>& row_counts, double alpha, int64_t b_group_div, int64_t cta_group,
           int64_t block_n, int64_t d_ptr_table, int64_t signal_ptr_table, int64_t wait_flags,
           int64_t wait_rows_per_flag, int64_t wait_flags_per_group, int64_t wait_target, int64_t max_ctas,
-          int64_t group_rot, int64_t group_mod) {
+          int64_t group_rot, int64_t group_mod, const c10::optional<at::Tensor>& scale_a,
+          const c10::optional<at::Tensor>& scale_b) {
   TORCH_CHECK(a.is_cuda() && b.is_cuda() && d.is_cuda(), "tutel_b200.gemm: CUDA tensors required");
   TORCH_CHECK(a.dim() == 3 && b.dim() == 3 && d.dim() == 3, "tutel_b200.gemm: expected 3-D operands");
   TORCH_CHECK(a.stride(2) == 1 && b.stride(2) == 1 && d.stride(2) == 1, "tutel_b200.gemm: innermost dim must be contiguous");
@@ -74,8 +75,9 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, bool a_mn, bo
   p.epilogue = static_cast<int>(epilogue);
   p.alpha = static_cast<float>(alpha);
   if (bias.has_value() && bias->defined()) {
-    TORCH_CHECK(bias->is_cuda() && bias->scalar_type() == a.scalar_type() && bias->dim() == 2 && bias->stride(1) == 1,
-                "tutel_b200.gemm: bias must be [Gb, N] of the input dtype");
+    TORCH_CHECK(bias->is_cuda() && bias->dim() == 2 && bias->stride(1) == 1 &&
+                    (bias->scalar_type() == a.scalar_type() || (a.element_size() == 1 && bias->scalar_type() == d.scalar_type() && d.element_size() == 2)),
+                "tutel_b200.gemm: bias must be [Gb, N] of the input dtype (fp8 inputs: of the 16-bit output dtype)");
     p.bias = bias->data_ptr();
     p.bias_group_stride = bias->stride(0);
   }
@@ -90,6 +92,18 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, bool a_mn, bo
   if (row_counts.has_value() && row_counts->defined()) {
     TORCH_CHECK(row_counts->is_cuda() && row_counts->scalar_type() == at::kInt && row_counts->numel() >= p.G);
     p.row_counts = row_counts->data_ptr<int>();
+  }
+  if (scale_a.has_value() && scale_a->defined()) {
+    TORCH_CHECK(scale_a->is_cuda() && scale_a->scalar_type() == at::kFloat && scale_a->dim() == 2 && scale_a->stride(1) == 1 &&
+                scale_a->size(0) == p.G && scale_a->size(1) == p.M, "tutel_b200.gemm: scale_a must be float [G, M]");
+    p.scale_a = scale_a->data_ptr<float>();
+    p.scale_a_group_stride = scale_a->stride(0);
+  }
+  if (scale_b.has_value() && scale_b->defined()) {
+    TORCH_CHECK(scale_b->is_cuda() && scale_b->scalar_type() == at::kFloat && scale_b->dim() == 2 && scale_b->stride(1) == 1 &&
+                scale_b->size(1) == p.N, "tutel_b200.gemm: scale_b must be float [Gb, N]");
+    p.scale_b = scale_b->data_ptr<float>();
+    p.scale_b_group_stride = scale_b->stride(0);
   }
   p.cta_group = static_cast<int>(cta_group);
   p.block_n = static_cast<int>(block_n);
@@ -211,6 +225,19 @@ std::vector<at::Tensor> gate_topk_forward(const at::Tensor& logits, int64_t k) {
   return {scores, idx, top, me, ce};
 }
 
+std::vector<at::Tensor> quantize_rows(const at::Tensor& x) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && x.dim() >= 2, "quantize_rows: contiguous CUDA tensor [.., K] expected");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int K = static_cast<int>(x.size(-1));
+  const int64_t R = x.numel() / K;
+  at::Tensor q = at::empty(x.sizes(), x.options().dtype(at::kFloat8_e4m3fn));
+  auto lead = x.sizes().vec();
+  lead.pop_back();
+  at::Tensor scale = at::empty(lead, x.options().dtype(at::kFloat));
+  TB_CHECK_CUDA(tb::quantize_rows_e4m3(x.data_ptr(), q.data_ptr(), scale.data_ptr<float>(), R, K, elem_type_of(x), cur_stream()));
+  return {q, scale};
+}
+
 at::Tensor skinny_gemm(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias,
                        const c10::optional<at::Tensor>& counts, bool w_is_kn, bool relu) {
   TORCH_CHECK(x.is_cuda() && w.is_cuda() && x.dim() == 3 && w.dim() == 3 && x.is_contiguous() && w.is_contiguous());
@@ -252,6 +279,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gate_grad", &gate_grad);
   m.def("gate_topk_forward", &gate_topk_forward);
   m.def("skinny_gemm", &skinny_gemm);
+  m.def("quantize_rows", &quantize_rows);
   register_symm_bindings(m);
   register_cpu_bindings(m);
   register_jit_bindings(m);

@@ -50,10 +50,15 @@ struct GemmArgs {
   const void* bias;
   long long bias_group_stride;
   int bias_is_fp32;
+  int bias_is_bf16;
   const void* aux;
   long long ld_aux, aux_group_stride;
 
   const int* row_counts;
+  const float* scale_a;  // [G, M] per-row dequantisation scales (fp8 operands), may be null
+  long long scale_a_group_stride;
+  const float* scale_b;  // [G / b_group_div, N] per-column scales, may be null
+  long long scale_b_group_stride;
 
   const uint32_t* wait_flags;
   int wait_rows_per_flag, wait_flags_per_group;
@@ -153,7 +158,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, bool is_bf16) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-template <int CG, bool A_MN, bool B_MN, int BN>
+template <int CG, bool A_MN, bool B_MN, int BN, int ELT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const GemmArgs args) {
@@ -200,7 +205,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);  // keep it in a uniform register
 
-  constexpr int kEltBytes = 2;                               // fp16 / bf16 operands (kind::f16)
+  constexpr int kEltBytes = ELT;                             // 2: fp16/bf16 (kind::f16)   1: e4m3/e5m2 (kind::f8f6f4)
+  static_assert(ELT == 2 || (!A_MN && !B_MN), "8-bit operands are K-major only");
   const int num_kb = (args.K * kEltBytes + kSwizzleBytes - 1) / kSwizzleBytes;
   constexpr int bk_elems = kSwizzleBytes / kEltBytes;        // K elements per stage
   const long long tile_step = gridDim.x / CG;
@@ -323,7 +329,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int k = 0; k < 4; ++k) {
               const uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + k * a_kstep);
               const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + k * b_kstep);
-              ptx::umma_f16<CG>(d_tmem, ad, bd, idesc, (kb | k) != 0);
+              if constexpr (ELT == 2) ptx::umma_f16<CG>(d_tmem, ad, bd, idesc, (kb | k) != 0);
+              else ptx::umma_f8<CG>(d_tmem, ad, bd, idesc, (kb | k) != 0);
             }
             ptx::umma_commit<CG>(empty_bar(s));                       // smem slot reusable once these retire
             if (kb == num_kb - 1) ptx::umma_commit<CG>(tfull_bar(acc));  // accumulator complete
@@ -381,6 +388,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         const int ncols = min(32, args.N - n);  // multiple of 8
+        if (args.scale_a != nullptr || args.scale_b != nullptr) {
+          // fp8 operands were quantised with one scale per A row and per B column: D = acc * sa[m] * sb[n]
+          const float sa = (args.scale_a != nullptr && row_ok)
+                               ? args.scale_a[static_cast<long long>(tc.g) * args.scale_a_group_stride + m] : 1.0f;
+          const float* sb = args.scale_b != nullptr ? args.scale_b + static_cast<long long>(gb) * args.scale_b_group_stride + n : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= (sb != nullptr && j < ncols) ? sa * sb[j] : sa;
+        }
 
         if (args.epilogue == EPI_NONE) {
           if (args.alpha != 1.0f) {
@@ -411,7 +426,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   f[0] = b0.x; f[1] = b0.y; f[2] = b0.z; f[3] = b0.w;
                   f[4] = b1.x; f[5] = b1.y; f[6] = b1.z; f[7] = b1.w;
                 } else {
-                  unpack8(*reinterpret_cast<const uint4*>(bias_g + (n + q * 8) * 2), ((args.idesc >> 7) & 7u) == 1u, f);
+                  unpack8(*reinterpret_cast<const uint4*>(bias_g + (n + q * 8) * 2), args.bias_is_bf16 != 0, f);
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[q * 8 + j] += f[j];
@@ -573,11 +588,11 @@ uint32_t make_idesc(int in_dtype, bool a_mn, bool b_mn, int umma_m, int umma_n) 
   return d;
 }
 
-template <int CG, bool A_MN, bool B_MN, int BN>
+template <int CG, bool A_MN, bool B_MN, int BN, int ELT>
 cudaError_t launch_inst(const CUtensorMap& ta, const CUtensorMap& tb_, const GemmArgs& args, int grid,
                         cudaStream_t stream) {
   using C = Cfg<CG, BN>;
-  auto* kern = gemm_sm100_kernel<CG, A_MN, B_MN, BN>;
+  auto* kern = gemm_sm100_kernel<CG, A_MN, B_MN, BN, ELT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -640,8 +655,11 @@ cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const c
   a.out_dtype = p.out_dtype;
   a.epilogue = p.epilogue; a.alpha = p.alpha;
   a.bias = p.bias; a.bias_group_stride = p.bias_group_stride; a.bias_is_fp32 = 0;
+  a.bias_is_bf16 = (eb == 2) ? (p.in_dtype == DT_BF16) : (p.out_dtype == DT_BF16);
   a.aux = p.aux; a.ld_aux = p.ld_aux; a.aux_group_stride = p.aux_group_stride;
   a.row_counts = p.row_counts;
+  a.scale_a = p.scale_a; a.scale_a_group_stride = p.scale_a_group_stride;
+  a.scale_b = p.scale_b; a.scale_b_group_stride = p.scale_b_group_stride;
   a.wait_flags = p.wait_flags; a.wait_rows_per_flag = p.wait_rows_per_flag > 0 ? p.wait_rows_per_flag : bm;
   a.wait_flags_per_group = p.wait_flags_per_group; a.wait_target = p.wait_target;
   a.signal_ptr_table = p.signal_ptr_table;
@@ -666,7 +684,7 @@ cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const c
   int grid = static_cast<int>(want < sms ? want : sms);
   if (cg == 2 && (grid & 1)) grid += 1;
 
-#define TB_LAUNCH(CGv, AMN, BMN, BNv) return launch_inst<CGv, AMN, BMN, BNv>(ta, tb_, a, grid, stream)
+#define TB_LAUNCH(CGv, AMN, BMN, BNv) return launch_inst<CGv, AMN, BMN, BNv, 2>(ta, tb_, a, grid, stream)
 #define TB_SWITCH_MAJOR(CGv, BNv)                                    \
   do {                                                               \
     if (!p.a_mn_major && !p.b_mn_major) TB_LAUNCH(CGv, false, false, BNv); \
@@ -674,6 +692,13 @@ cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const c
     if (p.a_mn_major && !p.b_mn_major) TB_LAUNCH(CGv, true, false, BNv);   \
     TB_LAUNCH(CGv, true, true, BNv);                                       \
   } while (0)
+  if (eb == 1) {
+    if (p.a_mn_major || p.b_mn_major) { *why = "fp8 operands must be K-major"; return cudaErrorInvalidValue; }
+    if (cg == 1 && bn == 256) return launch_inst<1, false, false, 256, 1>(ta, tb_, a, grid, stream);
+    if (cg == 1 && bn == 128) return launch_inst<1, false, false, 128, 1>(ta, tb_, a, grid, stream);
+    if (cg == 2 && bn == 256) return launch_inst<2, false, false, 256, 1>(ta, tb_, a, grid, stream);
+    if (cg == 2 && bn == 128) return launch_inst<2, false, false, 128, 1>(ta, tb_, a, grid, stream);
+  }
   if (cg == 1 && bn == 256) TB_SWITCH_MAJOR(1, 256);
   if (cg == 1 && bn == 128) TB_SWITCH_MAJOR(1, 128);
   if (cg == 2 && bn == 256) TB_SWITCH_MAJOR(2, 256);

@@ -47,6 +47,13 @@ struct GemmProblem {
   const void* aux = nullptr;  // [G, M, N] row-major, out_dtype
   long long ld_aux = 0, aux_group_stride = 0;
 
+  // fp8 (e4m3 / e5m2, K-major) operands: optional per-row scales of A [G, M] and per-column scales of B [G/div, N]
+  // (fp32); the epilogue computes D = acc * scale_a[m] * scale_b[n] before bias / activation.
+  const float* scale_a = nullptr;
+  long long scale_a_group_stride = 0;
+  const float* scale_b = nullptr;
+  long long scale_b_group_stride = 0;
+
   // Optional: valid rows per group (device int32[G]); row tiles past the count are skipped entirely
   // (dropless / Megablocks path: no host sync, no padded FLOPs).
   const int* row_counts = nullptr;

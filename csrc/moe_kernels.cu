@@ -15,6 +15,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include "ptx.cuh"
 
@@ -478,6 +479,48 @@ gate_topk_kernel(const float* __restrict__ logits, float* __restrict__ scores, i
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// per-row e4m3 quantisation (activations / K-major weights for the fp8 tcgen05 GEMM): one warp per row
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+quantize_rows_kernel(const T* __restrict__ x, uint8_t* __restrict__ q, float* __restrict__ scale, long long R, int K) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int VN = Vec<T>::N;
+  for (long long r = static_cast<long long>(blockIdx.x) * 8 + warp; r < R; r += static_cast<long long>(gridDim.x) * 8) {
+    const T* row = x + r * K;
+    float amax = 0.0f;
+    const int nv = K / VN;
+    for (int v = lane; v < nv; v += 32) {
+      float f[VN];
+      Vec<T>::unpack(ptx::ld_v4(reinterpret_cast<const uint4*>(row) + v), f);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) amax = fmaxf(amax, fabsf(f[i]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const float s = amax > 0.0f ? amax * (1.0f / 448.0f) : 1.0f;
+    const float inv = 1.0f / s;
+    if (lane == 0) scale[r] = s;
+    uint8_t* qrow = q + r * K;
+    for (int v = lane; v < nv; v += 32) {
+      float f[VN];
+      Vec<T>::unpack(ptx::ld_v4(reinterpret_cast<const uint4*>(row) + v), f);
+      uint32_t packed[VN / 4];
+#pragma unroll
+      for (int i = 0; i < VN / 4; ++i) {
+        const __nv_fp8x4_e4m3 p4(make_float4(f[4 * i] * inv, f[4 * i + 1] * inv, f[4 * i + 2] * inv, f[4 * i + 3] * inv));
+        packed[i] = *reinterpret_cast<const uint32_t*>(&p4);
+      }
+      if constexpr (VN == 8) {
+        *reinterpret_cast<uint2*>(qrow + static_cast<long long>(v) * 8) = make_uint2(packed[0], packed[1]);
+      } else {
+        *reinterpret_cast<uint32_t*>(qrow + static_cast<long long>(v) * 4) = packed[0];
+      }
+    }
+  }
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -614,6 +657,30 @@ cudaError_t gate_grad(const void* a, const void* buf, const int* idx, const int*
     case ET_BF16: return gate_grad_t<__nv_bfloat16>(a, buf, idx, loc, dgate, S, E, k, C, M, stream);
   }
   return cudaErrorInvalidValue;
+}
+
+cudaError_t quantize_rows_e4m3(const void* x, void* q, float* scale, long long R, int K, int elem_type,
+                               cudaStream_t stream) {
+  if (R <= 0 || K <= 0) return cudaSuccess;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(q) & 7)) return cudaErrorInvalidValue;
+  const long long want = (R + 7) / 8;
+  const int grid = static_cast<int>(want < 16LL * num_sms() ? want : 16LL * num_sms());
+  switch (elem_type) {
+    case ET_F32:
+      if (K % 4) return cudaErrorInvalidValue;
+      quantize_rows_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<uint8_t*>(q), scale, R, K);
+      break;
+    case ET_F16:
+      if (K % 8) return cudaErrorInvalidValue;
+      quantize_rows_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(x), static_cast<uint8_t*>(q), scale, R, K);
+      break;
+    case ET_BF16:
+      if (K % 8) return cudaErrorInvalidValue;
+      quantize_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(q), scale, R, K);
+      break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
 }
 
 cudaError_t gate_topk_forward(const float* logits, float* scores, int* idx, float* topk_scores, float* me_partial,

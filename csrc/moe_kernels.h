@@ -48,6 +48,11 @@ cudaError_t gate_grad(const void* a, const void* buf, const int* idx, const int*
 cudaError_t gate_topk_forward(const float* logits, float* scores, int* idx, float* topk_scores, float* me_partial,
                               int* ce_partial, int S, int E, int k, cudaStream_t stream);
 
+// q[r, :] = e4m3(x[r, :] / scale[r]),  scale[r] = max|x[r, :]| / 448   (one scale per row; rows are K-major GEMM
+// operands, so the scale factors out of the dot product and is applied in the GEMM epilogue).
+cudaError_t quantize_rows_e4m3(const void* x, void* q, float* scale, long long R, int K, int elem_type,
+                               cudaStream_t stream);
+
 // Dropless / decoder inference: y[g, r, :] = act(x[g, r, :] @ W[g] + bias[g]) for r < counts[g] (device counts, no
 // host sync); x [G, rows_cap, K], y [G, rows_cap, N], W [G, N, K] or (w_is_kn) [G, K, N].  Rows past the count are
 // left untouched.  (csrc/skinny_gemm.cu)

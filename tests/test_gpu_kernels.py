@@ -215,3 +215,40 @@ def test_dropless_fp32_many_experts_uses_skinny_path():
         b = layer(x, megablocks_size=1)
     assert backend.launch_count() - n0 >= 2
     assert torch.allclose(a, b, atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize('cg', [1, 2])
+def test_fp8_gemm_with_row_col_scales(C, cg):
+    from tutel_b200.ops import gemm as G
+    torch.manual_seed(6)
+    Gn, M, N, K = 2, 384, 272, 512
+    a = torch.randn(Gn, M, K, device='cuda').bfloat16() * torch.rand(Gn, M, 1, device='cuda').bfloat16() * 4
+    b = (torch.randn(Gn, N, K, device='cuda') * 0.1).bfloat16()
+    bias = torch.randn(Gn, N, device='cuda').bfloat16()
+    aq, sa = G.quantize_rows(a)
+    bq, sb = G.quantize_rows(b)
+    assert aq.dtype == torch.float8_e4m3fn and sa.shape == (Gn, M)
+    deq = aq.float() * sa.unsqueeze(-1)
+    assert (deq - a.float()).abs().max() <= a.float().abs().amax() * 0.07
+    d = G.raw_gemm(aq, bq, epilogue=G.EPI_BIAS_RELU, bias=bias, out_dtype=torch.bfloat16, scale_a=sa, scale_b=sb, cta_group=cg)
+    ref_q = torch.relu(torch.matmul(deq, (bq.float() * sb.unsqueeze(-1)).transpose(1, 2)) + bias.float().unsqueeze(1))
+    assert torch.allclose(d.float(), ref_q, atol=0.06, rtol=2e-2)          # exact up to bf16 output rounding
+    ref = torch.relu(torch.matmul(a.float(), b.float().transpose(1, 2)) + bias.float().unsqueeze(1))
+    assert (d.float() - ref).norm() / ref.norm() < 0.06                    # quantisation error budget
+
+
+def test_fp8_forward_layer_close_to_bf16():
+    from tutel_b200 import moe
+    def build(fp8):
+        torch.manual_seed(0)
+        return moe.moe_layer(gate_type={'type': 'top', 'k': 2}, model_dim=256, seeds=(1, 1, 1),
+                             experts={'type': 'ffn', 'num_experts_per_device': 4, 'hidden_size_per_expert': 512,
+                                      'activation_fn': lambda t: F.relu(t), 'fp8': fp8}).cuda().bfloat16()
+    a, b = build(False), build(True)
+    x = torch.randn(4, 128, 256, device='cuda', dtype=torch.bfloat16)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = a(xa), b(xb)
+    assert (yb.float() - ya.float()).norm() / ya.float().norm() < 0.08
+    ya.float().pow(2).mean().backward()
+    yb.float().pow(2).mean().backward()
+    assert (xb.grad.float() - xa.grad.float()).norm() / xa.grad.float().norm() < 0.15

@@ -22,7 +22,7 @@ from ...parallel import communicate as C
 
 class FusedExpertsNetwork(torch.nn.Module):
     def __init__(self, model_dim, hidden_size_per_expert, num_experts_per_device, sharded_count, activation_fn=None,
-                 activation_fn_with_self=None, output_dim=None, has_fc1_bias=True, has_fc2_bias=True):
+                 activation_fn_with_self=None, output_dim=None, has_fc1_bias=True, has_fc2_bias=True, fp8=None):
         super().__init__()
         self.skip_expert = int(os.environ.get('SKIP_EXPERT', '0')) != 0
         assert hidden_size_per_expert % sharded_count == 0, \
@@ -33,6 +33,8 @@ class FusedExpertsNetwork(torch.nn.Module):
         self.sharded_count = sharded_count
         self.hidden_size = hidden_size_per_expert // sharded_count
         self.output_dim = output_dim or model_dim
+        # fp8=True (or TUTEL_B200_FP8=1): expert GEMMs of the FORWARD pass run in e4m3 with per-row / per-channel scales
+        self.fp8 = bool(int(os.environ.get('TUTEL_B200_FP8', '0'))) if fp8 is None else bool(fp8)
 
         if activation_fn_with_self is not None:
             assert activation_fn is None, 'Option `activation_fn_with_self` has been specified, please keep exactly one of them.'
@@ -133,7 +135,10 @@ class FusedExpertsNetwork(torch.nn.Module):
                 y = self.activation_fn(y)
             return G.skinny_linear(y, w2, b2, 'kn', row_counts)
         if self._act_kind == 'relu' and G.can_use_tcgen05(x, w1) and G.can_use_tcgen05(x, w2):
-            y = G.fused_relu_ffn(x, w1, b1, w2, b2, row_counts)
+            if self.fp8 and x.size(-1) % 16 == 0 and w1.size(1) % 16 == 0:
+                y = G.fused_relu_ffn_fp8(x, w1, b1, w2, b2, row_counts)
+            else:
+                y = G.fused_relu_ffn(x, w1, b1, w2, b2, row_counts)
         else:
             y = G.grouped_linear(x, w1, b1, 'nk', row_counts)
             y = self.activation_fn(y)

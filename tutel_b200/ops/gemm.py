@@ -38,7 +38,8 @@ def raw_gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool
              out_dtype: Optional[torch.dtype] = None, alpha: float = 1.0, b_group_div: int = 1, cta_group: int = 0,
              block_n: int = 0, d_ptr_table: int = 0, signal_ptr_table: int = 0, wait_flags: int = 0,
              wait_rows_per_flag: int = 0, wait_flags_per_group: int = 0, wait_target: int = 0,
-             max_ctas: int = 0, group_rot: int = 0, group_mod: int = 1) -> torch.Tensor:
+             max_ctas: int = 0, group_rot: int = 0, group_mod: int = 1, scale_a: Optional[torch.Tensor] = None,
+             scale_b: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D[g] = epilogue(A[g] @ B[g // b_group_div]).
 
     ``a``: ``[G, M, K]`` (or ``[G, K, M]`` when ``a_mn``);  ``b``: ``[Gb, N, K]`` (or ``[Gb, K, N]`` when ``b_mn``).
@@ -49,18 +50,21 @@ def raw_gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool
     M = a.size(2) if a_mn else a.size(1)
     N = b.size(2) if b_mn else b.size(1)
     if out is None:
-        out = torch.empty([G, M, N], dtype=out_dtype or a.dtype, device=a.device)
+        if out_dtype is None:
+            out_dtype = a.dtype if a.element_size() > 1 else torch.bfloat16
+        out = torch.empty([G, M, N], dtype=out_dtype, device=a.device)
     d = out if out.dim() == 3 else out.unsqueeze(0)
     if bias is not None:
         bias = bias.reshape(b.size(0), N)
-        if bias.stride(-1) != 1 or bias.dtype != a.dtype:
-            bias = bias.to(a.dtype).contiguous()
+        want = a.dtype if a.element_size() > 1 else out.dtype
+        if bias.stride(-1) != 1 or bias.dtype != want:
+            bias = bias.to(want).contiguous()
     if aux is not None:
         aux = _prep(aux)
     backend.count_launch()
     C.gemm(a, b, d, a_mn, b_mn, epilogue, bias, aux, row_counts, float(alpha), int(b_group_div), int(cta_group),
            int(block_n), int(d_ptr_table), int(signal_ptr_table), int(wait_flags), int(wait_rows_per_flag),
-           int(wait_flags_per_group), int(wait_target), int(max_ctas), int(group_rot), int(group_mod))
+           int(wait_flags_per_group), int(wait_target), int(max_ctas), int(group_rot), int(group_mod), scale_a, scale_b)
     return out
 
 
@@ -210,3 +214,59 @@ def skinny_linear(x, w, bias, w_layout, row_counts, relu=False):
     backend.count_launch()
     b = None if bias is None else bias.reshape(w.size(0), -1).contiguous()
     return backend.require_ext().skinny_gemm(x.contiguous(), w.contiguous(), b, row_counts, w_layout == 'kn', relu)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fp8 (e4m3) forward path: per-row activation scales x per-output-channel weight scales, applied in the epilogue
+# ----------------------------------------------------------------------------------------------------------------
+_FP8_WEIGHT_CACHE = {}
+
+
+def quantize_rows(x: torch.Tensor):
+    """(q e4m3 [.., K], scale fp32 [..]) with one scale per row (native kernel)."""
+    backend.count_launch()
+    return backend.require_ext().quantize_rows(x.contiguous())
+
+
+def fp8_weight(w: torch.Tensor, layout: str):
+    """K-major e4m3 copy [G, N, K] + per-output-channel scales [G, N] of a weight in 'nk' or 'kn' layout.
+    Cached per (storage, version): weights are re-quantised only after they changed."""
+    key = (w.data_ptr(), layout, tuple(w.shape))
+    ver = w._version
+    hit = _FP8_WEIGHT_CACHE.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1], hit[2]
+    wk = w.detach() if layout == 'nk' else w.detach().transpose(1, 2)
+    q, s = quantize_rows(wk.contiguous())
+    _FP8_WEIGHT_CACHE[key] = (ver, q, s)
+    return q, s
+
+
+def fp8_linear(x: torch.Tensor, w: torch.Tensor, bias, w_layout: str, epilogue: int = None, row_counts=None):
+    """y = act(x @ W + b) with both operands quantised to e4m3 on the fly; result in x.dtype."""
+    xq, sx = quantize_rows(x)
+    wq, sw = fp8_weight(w, w_layout)
+    if epilogue is None:
+        epilogue = EPI_BIAS if bias is not None else EPI_NONE
+    return raw_gemm(xq, wq, epilogue=epilogue, bias=bias, row_counts=row_counts, out_dtype=x.dtype, scale_a=sx, scale_b=sw)
+
+
+class FusedReluFFNFp8(torch.autograd.Function):
+    """fp8 forward (2x tensor-core rate), bf16 backward on the master weights (same launches as FusedReluFFN)."""
+
+    @staticmethod
+    def forward(ctx: Any, x, w1, b1, w2, b2, row_counts):
+        act = fp8_linear(x, w1, b1, 'nk', EPI_BIAS_RELU, row_counts)
+        y = fp8_linear(act, w2, b2, 'kn', None, row_counts)
+        ctx.save_for_backward(x, w1, w2, act)
+        ctx.has_b1, ctx.has_b2 = b1 is not None, b2 is not None
+        ctx.row_counts = row_counts
+        return y
+
+    backward = FusedReluFFN.backward
+
+
+def fused_relu_ffn_fp8(x, w1, b1, w2, b2, row_counts=None):
+    b1 = None if b1 is None else b1.reshape(w1.size(0), -1)
+    b2 = None if b2 is None else b2.reshape(w2.size(0), -1)
+    return FusedReluFFNFp8.apply(x, w1, b1, w2, b2, row_counts)
