@@ -12,8 +12,10 @@ from ...parallel import communicate as C
 
 class LlamaFFNNetwork(torch.nn.Module):
     def __init__(self, model_dim, hidden_size_per_expert, num_experts_per_device, sharded_count,
-                 activation_fn=torch.nn.functional.silu):
+                 activation_fn=torch.nn.functional.silu, fp8=None):
         super().__init__()
+        import os
+        self.fp8 = bool(int(os.environ.get('TUTEL_B200_FP8', '0'))) if fp8 is None else bool(fp8)
         self.sharded_count = sharded_count
         self.full_shapes = {
             'W_fc1': torch.Size([num_experts_per_device, model_dim, hidden_size_per_expert]),
@@ -42,9 +44,9 @@ class LlamaFFNNetwork(torch.nn.Module):
         w1, w2, w3 = (self._full(n, ctx.group) for n in ('W_fc1', 'W_fc2', 'W_fc3'))
         if x.dim() > 3:
             x = x.reshape(x.size(0), x.size(1), -1)
-        y1 = G.grouped_linear(x, w1, None, 'kn')
-        y2 = G.grouped_linear(x, w2, None, 'kn')
-        return G.grouped_linear(self.activation_fn(y1) * y2, w3, None, 'kn')
+        y1 = G.grouped_linear(x, w1, None, 'kn', fp8=self.fp8)
+        y2 = G.grouped_linear(x, w2, None, 'kn', fp8=self.fp8)
+        return G.grouped_linear(self.activation_fn(y1) * y2, w3, None, 'kn', fp8=self.fp8)
 
     def extra_repr(self):
         return 'full shapes: %s, sharded_count=%d' % ({k: tuple(v) for k, v in self.full_shapes.items()}, self.sharded_count)

@@ -82,11 +82,13 @@ class GroupedLinear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx: Any, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], w_layout: str,
-                row_counts: Optional[torch.Tensor]):
+                row_counts: Optional[torch.Tensor], fp8: bool = False):
         ctx.w_layout = w_layout
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, w)
         ctx.row_counts = row_counts
+        if fp8:     # e4m3 forward, bf16/fp16 backward on the master weights
+            return fp8_linear(x, w, bias, w_layout, None, row_counts)
         return raw_gemm(x, w, b_mn=(w_layout == 'kn'), epilogue=EPI_BIAS if bias is not None else EPI_NONE, bias=bias,
                         row_counts=row_counts)
 
@@ -108,7 +110,7 @@ class GroupedLinear(torch.autograd.Function):
                 dw = raw_gemm(dy, x, a_mn=True, b_mn=True)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum(dim=1, dtype=torch.float32).to(dy.dtype)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 def _zero_tail(t: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
@@ -117,11 +119,12 @@ def _zero_tail(t: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
 
 
 def grouped_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, w_layout: str = 'nk',
-                   row_counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   row_counts: Optional[torch.Tensor] = None, fp8: bool = False) -> torch.Tensor:
     """Batched per-expert linear layer; falls back to ``torch.matmul`` for dtypes/devices the kernel does not cover."""
     if can_use_tcgen05(x, w) and (bias is None or bias.numel() == w.size(0) * (w.size(1) if w_layout == 'nk' else w.size(2))):
         b = None if bias is None else bias.reshape(w.size(0), -1)
-        return GroupedLinear.apply(x, w, b, w_layout, row_counts)
+        fp8 = fp8 and x.size(-1) % 16 == 0
+        return GroupedLinear.apply(x, w, b, w_layout, row_counts, fp8)
     y = torch.matmul(x, w.transpose(1, 2) if w_layout == 'nk' else w)
     if bias is not None:
         y = y + bias.reshape(w.size(0), 1, -1)
