@@ -13,8 +13,10 @@ def gshard_loss(scores_w_noise, top_ids):
     """GShard loss: sum_e mean-score(e) * fraction-of-first-choices(e) * E  (uses the first choice only)."""
     num_samples, num_experts = int(scores_w_noise.size(0)), int(scores_w_noise.size(1))
     first = top_ids[:, 0] if top_ids.dim() == 2 else top_ids
-    ce = torch.bincount(first.reshape(-1).to(torch.int64), minlength=num_experts).to(scores_w_noise.dtype)
-    ce = ce * (num_experts / num_samples)
+    # histogram without torch.bincount (which synchronises with the host to size its output)
+    ce = torch.zeros([num_experts], dtype=torch.float32, device=scores_w_noise.device)
+    ce.scatter_add_(0, first.reshape(-1).to(torch.int64), torch.ones([first.numel()], dtype=torch.float32, device=ce.device))
+    ce = ce.to(scores_w_noise.dtype) * (num_experts / num_samples)
     me = torch.sum(scores_w_noise, dim=0)
     return torch.sum(me * ce) / num_samples
 

@@ -189,14 +189,15 @@ def simple_all_reduce(input: torch.Tensor, group=None, op=dist.ReduceOp.SUM, inp
     return output
 
 
-def simple_all_to_all(input: torch.Tensor, group=None, background: bool = False):
+def simple_all_to_all(input: torch.Tensor, group=None, background: bool = False, _alias_ok: bool = False):
     world_size = get_world_size(group)
     input = input.contiguous()
     if world_size == 1 or TUTEL_SKIP_A2A:
         return input if not background else (input, lambda *a: None)
     t = _p2p(group, input)
     if t is not None and not background and input.numel() % world_size == 0:
-        return t.all_to_all(input)
+        # `_alias_ok`: the caller copies the result out of the (re-used) staging area itself
+        return t.all_to_all(input, copy=not _alias_ok)
     output = torch.empty_like(input)
     if background:
         work = dist.all_to_all_single(output, input, group=group, async_op=True)
@@ -340,7 +341,7 @@ def _raw_all_to_all(packed: torch.Tensor, group, use_2dh: bool) -> torch.Tensor:
     """All-to-all of a [W, ...] tensor along dim 0."""
     world = get_world_size(group)
     if not use_2dh:
-        return simple_all_to_all(packed, group)
+        return simple_all_to_all(packed, group, _alias_ok=True)
     nnodes, ngpus = _hier_sizes(world)
     if nnodes == 1 or ngpus == 1 or (group is not None and group is not dist.group.WORLD and world != get_world_size()):
         # One NVSwitch domain (or one GPU per node): the 2-D hierarchical algorithm degenerates to the flat
@@ -365,7 +366,13 @@ class _AllToAll(torch.autograd.Function):
     def forward(ctx: Any, x: torch.Tensor, input_dim: int, output_dim: int, group, use_2dh: bool):
         ctx.dims, ctx.group, ctx.use_2dh = (input_dim, output_dim), group, use_2dh
         world = get_world_size(group)
-        return _a2a_unpack(_raw_all_to_all(_a2a_pack(x, output_dim, world), group, use_2dh), input_dim)
+        raw = _raw_all_to_all(_a2a_pack(x, output_dim, world), group, use_2dh)
+        out = _a2a_unpack(raw, input_dim)
+        if out.is_cuda and out.untyped_storage().data_ptr() == raw.untyped_storage().data_ptr():
+            t = _p2p(group, out)
+            if t is not None and t.owns(raw):
+                out = out.clone()          # still a view of the P2P staging area: detach it before the next collective
+        return out
 
     @staticmethod
     def backward(ctx: Any, dy: torch.Tensor):

@@ -147,6 +147,11 @@ class P2PTransport:
         r = self.rank if rank is None else rank
         return self.heap.tensor(r, off, list(shape), dtype, self.device)
 
+    def owns(self, tensor: torch.Tensor) -> bool:
+        """True when `tensor` lives inside this rank's arena (e.g. a zero-copy view of the staging region)."""
+        base = self.heap.base_ptr(self.rank)
+        return base <= tensor.data_ptr() < base + self.heap_bytes
+
     def base_ptr(self, rank: int) -> int:
         return self.heap.base_ptr(rank)
 
