@@ -35,6 +35,8 @@ def parse():
     ap.add_argument('--top', type=int, default=TOP_K)
     ap.add_argument('--overlap', type=int, default=1)
     ap.add_argument('--no_e2e', action='store_true')
+    ap.add_argument('--expert_type', type=str, default='ffn')     # llama_ffn: Mixtral-style SwiGLU block (BASELINE config #3)
+    ap.add_argument('--fp8', action='store_true')                  # ours only: e4m3 forward GEMMs
     return ap.parse_args()
 
 
@@ -74,8 +76,10 @@ def main():
             super().__init__()
             self._moe_layer = moe_api.moe_layer(
                 gate_type={'type': 'top', 'k': args.top, 'fp32_gate': False, 'capacity_factor': 1.0},
-                experts={'type': 'ffn', 'num_experts_per_device': local_experts, 'hidden_size_per_expert': args.hidden,
-                         'activation_fn': lambda x: F.relu(x)},
+                experts=dict({'type': args.expert_type, 'num_experts_per_device': local_experts,
+                              'hidden_size_per_expert': args.hidden},
+                             **({'activation_fn': (lambda x: F.relu(x))} if args.expert_type == 'ffn' else {}),
+                             **({'fp8': True} if (args.fp8 and args.impl == 'ours') else {})),
                 model_dim=args.model_dim,
                 scan_expert_func=lambda name, param: setattr(param, 'skip_allreduce', True),
                 seeds=(1, rank + 1, 1),
@@ -171,13 +175,15 @@ def main():
 
     tokens = world * BATCH * TOKENS * args.steps
     value = tokens / (ms * 1e-3)
-    flops = 4.0 * 3 * BATCH * TOKENS * args.model_dim * args.hidden * min(args.top, args.experts)  # per GPU per step
+    mats = 3 if args.expert_type == 'llama_ffn' else 2
+    flops = 2.0 * mats * 3 * BATCH * TOKENS * args.model_dim * args.hidden * min(args.top, args.experts)  # per GPU per step
     out = {
         'metric': 'moe_layer_fwd_bwd_tokens_per_sec', 'value': value, 'unit': 'tokens/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic (random tokens, random-init weights)',
         'impl': args.impl,
-        'config': {'model': 'helloworld moe_layer top-%d %d-expert ffn(relu) model_dim=%d hidden=%d' % (args.top, args.experts, args.model_dim, args.hidden),
+        'config': {'model': 'helloworld moe_layer top-%d %d-expert %s%s model_dim=%d hidden=%d' % (
+            args.top, args.experts, 'ffn(relu)' if args.expert_type == 'ffn' else args.expert_type, ' fp8-forward' if args.fp8 else '', args.model_dim, args.hidden),
                    'global_batch': world * BATCH, 'seq_len': TOKENS, 'tokens_per_gpu': BATCH * TOKENS,
                    'parallelism': 'ep%d (%d local experts/GPU)' % (world, local_experts), 'capacity_factor': 1.0,
                    'step': 'zero_grad + fwd + nll_loss + bwd + gate-grad all-reduce + SGD',
