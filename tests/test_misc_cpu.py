@@ -1,0 +1,74 @@
+"""System utilities, compat shim, launcher argument plumbing, activation classification."""
+import os
+import subprocess
+import sys
+
+import torch
+import torch.nn.functional as F
+
+from helpers import ROOT
+
+
+def test_system_utils(tmp_path):
+    from tutel_b200 import system
+    assert system.apply_rank_size_from_pattern(str(tmp_path / 'a/{rank}-of-{size}.ckpt'), 3, 8).endswith('a/3-of-8.ckpt')
+    assert os.path.isdir(tmp_path / 'a')
+    t = torch.arange(6.).view(2, 3)
+    system.save(t, str(tmp_path / 't.npy'))
+    assert torch.equal(system.load(str(tmp_path / 't.npy')), t)
+    c = system.cache()
+    c.reset(); c.set('x', 1); c.set('y', 2)
+    assert c.get('x') == 1 and sorted(c.get()) == [1, 2]
+    assert system.record_time(is_cuda=False) > 0
+    system.init_affinity_at_program_beginning()          # must not raise
+
+
+def test_compat_shim_runs_reference_style_code():
+    code = r'''
+import tutel_b200.compat as compat
+compat.install_as_tutel()
+import torch, torch.nn.functional as F
+from tutel import moe as tutel_moe, net, system, jit
+from tutel.impls.fast_dispatch import extract_critical, fast_encode
+from tutel.impls import communicate as C
+from tutel.experts.ffn import ExpertModule
+from tutel.gates.top import Gate
+env = system.init_data_model_parallel(backend='gloo')
+layer = tutel_moe.moe_layer(gate_type={'type': 'top', 'k': 2}, model_dim=8,
+                            experts={'type': 'ffn', 'count_per_node': 2, 'hidden_size_per_expert': 8, 'activation_fn': lambda x: F.relu(x)})
+y = layer(torch.randn(4, 8))
+assert y.shape == (4, 8) and C.get_world_size() == 1 and net.simple_all_reduce(y) is y
+print('COMPAT_OK')
+'''
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    p = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=300)
+    assert 'COMPAT_OK' in p.stdout, p.stdout + p.stderr
+
+
+def test_activation_classification():
+    from tutel_b200.ops.gemm import classify_activation
+    assert classify_activation(None) == 'relu' and classify_activation(F.relu) == 'relu'
+    assert classify_activation(lambda x: F.relu(x)) == 'relu'
+    assert classify_activation(lambda x: F.gelu(x)) is None
+    drop = torch.nn.Dropout(0.5)
+    assert classify_activation(lambda x: drop(F.relu(x))) is None      # stochastic -> never fused
+
+
+def test_launcher_builds_torchrun_command(monkeypatch):
+    from tutel_b200.launcher import run
+    seen = {}
+    monkeypatch.setattr(os, 'execvpe', lambda f, a, e: seen.update(cmd=a, env=dict(e)))
+    monkeypatch.setattr(sys, 'argv', ['run', '-m', 'my.prog', '--flag'])
+    monkeypatch.setenv('OMPI_COMM_WORLD_SIZE', '2')
+    monkeypatch.setenv('OMPI_COMM_WORLD_RANK', '1')
+    monkeypatch.setenv('LOCAL_SIZE', '4')
+    run.main()
+    cmd = seen['cmd']
+    assert '--nproc_per_node=4' in cmd and '--nnodes=2' in cmd and '--node_rank=1' in cmd
+    assert cmd[-3:] == ['-m', 'my.prog', '--flag'] and 'tutel_b200.launcher.execl' in cmd
+    from tutel_b200.launcher import execl
+    monkeypatch.setattr(sys, 'argv', ['execl', '-m', 'my.prog'])
+    monkeypatch.setenv('TUTEL_CUDA_SANDBOX', '2')
+    monkeypatch.setenv('LOCAL_RANK', '3')
+    execl.main()
+    assert seen['env']['CUDA_VISIBLE_DEVICES'] == '3' and seen['cmd'][-2:] == ['-m', 'my.prog']
