@@ -22,9 +22,7 @@ run bench_ours bench.py --gpus $N --steps 20 --warmup 5
 run bench_reference bench.py --impl reference --gpus $N --steps 20 --warmup 5
 TUTEL_B200_FUSED=0 run bench_ours_unfused bench.py --gpus $N --steps 20 --warmup 5
 if [ "$MODE" = "full" ]; then
-  TUTEL_B200_COMM=nccl TUTEL_B200_FUSED=0 run bench_ours_nccl bench.py --gpus $N --steps 20 --warmup 5
   run mixtral_ours_fp8_d2 bench.py --gpus $N --steps 10 --warmup 3 --expert_type llama_ffn --fp8 --overlap 2
-  run mixtral_ours_bf16_d2 bench.py --gpus $N --steps 10 --warmup 3 --expert_type llama_ffn --overlap 2
   run mixtral_reference_bf16_d2 bench.py --impl reference --gpus $N --steps 10 --warmup 3 --expert_type llama_ffn --overlap 2
   P=$((P+1)); timeout 300 $T --master-port $P -m tutel_b200.examples.bandwidth_test --sweep --compare_nccl --loop 10 --json $OUT/a2a_sweep.json > $OUT/a2a_sweep.log 2>&1
   grep -E "all_to_all" $OUT/a2a_sweep.log | tail -8
