@@ -87,7 +87,7 @@ def run_gemm(c):
         counts = torch.tensor(c['counts'], device=dev, dtype=torch.int32)
 
     def call():
-        _C.gemm(a_op, b_op, d, c['a_mn'], c['b_mn'], epi, bias, aux, counts, 1.0, 1, c['cg'], c['bn'], 0, 0, 0, 0, 0, 0, 0, 0, 1, None, None)
+        _C.gemm(a_op, b_op, d, c['a_mn'], c['b_mn'], epi, bias, aux, counts, 1.0, 1, c['cg'], c['bn'], 0, 0, 0, 0, 0, 0, 0, 0, 1, None, None, None)
 
     call()
     torch.cuda.synchronize()

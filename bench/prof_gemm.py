@@ -14,9 +14,9 @@ for it in range(3):
     if it == 2:
         torch.cuda.synchronize(); torch.cuda.cudart().cudaProfilerStart()
     if which in ('all', 'cg2'):
-        _C.gemm(a, b, d, False, False, 0, None, None, None, 1.0, 1, 2, 256, 0, 0, 0, 0, 0, 0, 0, 0, 1, None, None)
+        _C.gemm(a, b, d, False, False, 0, None, None, None, 1.0, 1, 2, 256, 0, 0, 0, 0, 0, 0, 0, 0, 1, None, None, None)
     if which in ('all', 'cg1'):
-        _C.gemm(a, b, d, False, False, 0, None, None, None, 1.0, 1, 1, 256, 0, 0, 0, 0, 0, 0, 0, 0, 1, None, None)
+        _C.gemm(a, b, d, False, False, 0, None, None, None, 1.0, 1, 1, 256, 0, 0, 0, 0, 0, 0, 0, 0, 1, None, None, None)
     if which in ('all', 'cublas'):
         torch.matmul(a, b.transpose(1, 2), out=d)
 torch.cuda.synchronize(); torch.cuda.cudart().cudaProfilerStop()

@@ -51,7 +51,7 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, bool a_mn, bo
           int64_t block_n, int64_t d_ptr_table, int64_t signal_ptr_table, int64_t wait_flags,
           int64_t wait_rows_per_flag, int64_t wait_flags_per_group, int64_t wait_target, int64_t max_ctas,
           int64_t group_rot, int64_t group_mod, const c10::optional<at::Tensor>& scale_a,
-          const c10::optional<at::Tensor>& scale_b) {
+          const c10::optional<at::Tensor>& scale_b, const c10::optional<at::Tensor>& colsum) {
   TORCH_CHECK(a.is_cuda() && b.is_cuda() && d.is_cuda(), "tutel_b200.gemm: CUDA tensors required");
   TORCH_CHECK(a.dim() == 3 && b.dim() == 3 && d.dim() == 3, "tutel_b200.gemm: expected 3-D operands");
   TORCH_CHECK(a.stride(2) == 1 && b.stride(2) == 1 && d.stride(2) == 1, "tutel_b200.gemm: innermost dim must be contiguous");
@@ -104,6 +104,12 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, bool a_mn, bo
                 scale_b->size(1) == p.N, "tutel_b200.gemm: scale_b must be float [Gb, N]");
     p.scale_b = scale_b->data_ptr<float>();
     p.scale_b_group_stride = scale_b->stride(0);
+  }
+  if (colsum.has_value() && colsum->defined()) {
+    TORCH_CHECK(colsum->is_cuda() && colsum->scalar_type() == at::kFloat && colsum->dim() == 2 && colsum->stride(1) == 1 &&
+                colsum->size(1) == p.N, "tutel_b200.gemm: colsum must be float [Gb, N]");
+    p.colsum = colsum->data_ptr<float>();
+    p.colsum_group_stride = colsum->stride(0);
   }
   p.cta_group = static_cast<int>(cta_group);
   p.block_n = static_cast<int>(block_n);

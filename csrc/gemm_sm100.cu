@@ -55,6 +55,8 @@ struct GemmArgs {
   long long ld_aux, aux_group_stride;
 
   const int* row_counts;
+  float* colsum;  // [G / b_group_div, N] fp32: += column sums of the epilogue result (bias gradient), may be null
+  long long colsum_group_stride;
   const float* scale_a;  // [G, M] per-row dequantisation scales (fp8 operands), may be null
   long long scale_a_group_stride;
   const float* scale_b;  // [G / b_group_div, N] per-column scales, may be null
@@ -445,6 +447,25 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
 
+        if (args.colsum != nullptr) {
+          // Bias gradient fused into the epilogue: transpose-reduce the warp's 32 rows x 32 columns with 31 shuffles
+          // (afterwards lane j holds the sum of column j) and add it to the fp32 accumulator in global memory.
+          float s[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s[j] = row_ok ? v[j] : 0.0f;
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send = upper ? s[i] : s[i + off];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+              s[i] = (upper ? s[i + off] : s[i]) + recv;
+            }
+          }
+          if (lane < ncols)
+            atomicAdd(args.colsum + static_cast<long long>(gb) * args.colsum_group_stride + n + lane, s[0]);
+        }
         if (staged) {
           // registers -> padded smem row (this thread's own) -> one asynchronous bulk store of the row segment
           const uint32_t slot = epi_base + static_cast<uint32_t>(ew * 2 + (c & 1)) * C::EPI_SLOT_BYTES +
@@ -658,6 +679,7 @@ cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const c
   a.bias_is_bf16 = (eb == 2) ? (p.in_dtype == DT_BF16) : (p.out_dtype == DT_BF16);
   a.aux = p.aux; a.ld_aux = p.ld_aux; a.aux_group_stride = p.aux_group_stride;
   a.row_counts = p.row_counts;
+  a.colsum = p.colsum; a.colsum_group_stride = p.colsum_group_stride;
   a.scale_a = p.scale_a; a.scale_a_group_stride = p.scale_a_group_stride;
   a.scale_b = p.scale_b; a.scale_b_group_stride = p.scale_b_group_stride;
   a.wait_flags = p.wait_flags; a.wait_rows_per_flag = p.wait_rows_per_flag > 0 ? p.wait_rows_per_flag : bm;

@@ -54,6 +54,11 @@ struct GemmProblem {
   const float* scale_b = nullptr;
   long long scale_b_group_stride = 0;
 
+  // Optional: fp32 [G/div, N] accumulator that receives (atomically) the column sums of the stored result - the bias
+  // gradient of the layer, fused into the dgrad GEMM instead of a separate reduction pass.  Must be zeroed by the caller.
+  float* colsum = nullptr;
+  long long colsum_group_stride = 0;
+
   // Optional: valid rows per group (device int32[G]); row tiles past the count are skipped entirely
   // (dropless / Megablocks path: no host sync, no padded FLOPs).
   const int* row_counts = nullptr;

@@ -13,7 +13,7 @@ def C():
 
 
 def _gemm(C, a, b, d, a_mn, b_mn, epi=0, bias=None, aux=None, counts=None, cg=0, bn=0):
-    C.gemm(a, b, d, a_mn, b_mn, epi, bias, aux, counts, 1.0, 1, cg, bn, 0, 0, 0, 0, 0, 0, 0, 0, 1, None, None)
+    C.gemm(a, b, d, a_mn, b_mn, epi, bias, aux, counts, 1.0, 1, cg, bn, 0, 0, 0, 0, 0, 0, 0, 0, 1, None, None, None)
 
 
 @pytest.mark.parametrize('cg', [1, 2])

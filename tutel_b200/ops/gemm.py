@@ -39,7 +39,7 @@ def raw_gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool
              block_n: int = 0, d_ptr_table: int = 0, signal_ptr_table: int = 0, wait_flags: int = 0,
              wait_rows_per_flag: int = 0, wait_flags_per_group: int = 0, wait_target: int = 0,
              max_ctas: int = 0, group_rot: int = 0, group_mod: int = 1, scale_a: Optional[torch.Tensor] = None,
-             scale_b: Optional[torch.Tensor] = None) -> torch.Tensor:
+             scale_b: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D[g] = epilogue(A[g] @ B[g // b_group_div]).
 
     ``a``: ``[G, M, K]`` (or ``[G, K, M]`` when ``a_mn``);  ``b``: ``[Gb, N, K]`` (or ``[Gb, K, N]`` when ``b_mn``).
@@ -64,7 +64,7 @@ def raw_gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool
     backend.count_launch()
     C.gemm(a, b, d, a_mn, b_mn, epilogue, bias, aux, row_counts, float(alpha), int(b_group_div), int(cta_group),
            int(block_n), int(d_ptr_table), int(signal_ptr_table), int(wait_flags), int(wait_rows_per_flag),
-           int(wait_flags_per_group), int(wait_target), int(max_ctas), int(group_rot), int(group_mod), scale_a, scale_b)
+           int(wait_flags_per_group), int(wait_target), int(max_ctas), int(group_rot), int(group_mod), scale_a, scale_b, colsum)
     return out
 
 
@@ -156,7 +156,9 @@ class FusedReluFFN(torch.autograd.Function):
         if rc is not None:
             dy = _zero_tail(dy, rc)
         # dh[T,H] = (dy[T,Mout] @ W2^T) * (act > 0)           W2 [H,Mout] is "nk" for this product
-        dh = raw_gemm(dy, w2, epilogue=EPI_RELU_BWD, aux=act, row_counts=rc)
+        want_db1 = ctx.has_b1 and ctx.needs_input_grad[2]
+        db1_acc = torch.zeros([w1.size(0), w1.size(1)], dtype=torch.float32, device=dy.device) if want_db1 else None
+        dh = raw_gemm(dy, w2, epilogue=EPI_RELU_BWD, aux=act, row_counts=rc, colsum=db1_acc)   # db1 fused in the epilogue
         if rc is not None:
             dh = _zero_tail(dh, rc)
             act = _zero_tail(act, rc)
@@ -166,7 +168,7 @@ class FusedReluFFN(torch.autograd.Function):
         if dx is not None and rc is not None:
             dx = _zero_tail(dx, rc)
         dw1 = raw_gemm(dh, x, a_mn=True, b_mn=True) if ctx.needs_input_grad[1] else None        # [H,M] = dh^T @ x
-        db1 = dh.sum(dim=1, dtype=torch.float32).to(dh.dtype) if ctx.has_b1 and ctx.needs_input_grad[2] else None
+        db1 = db1_acc.to(dh.dtype) if want_db1 else None
         return dx, dw1, db1, dw2, db2, None
 
 

@@ -85,7 +85,7 @@ class FusedEngine:
         self.clock = 0
         self.side = torch.cuda.Stream()
         self.chunk_counters = torch.zeros([self.E * _FLAGS_PER_SEG], dtype=torch.int32, device='cuda')
-        self.disabled_for: set = set()
+        self.warned = False
 
     # ---- buffer ring ------------------------------------------------------------------------------------------
     def acquire(self, C: int, hold: bool) -> Optional[_BufferSet]:
@@ -165,21 +165,28 @@ def engine_for(layer, x: torch.Tensor, crit, d: int):
         layer.__dict__['_tb_fused_state'] = eng        # kept on the layer itself (id() values get recycled)
     if eng is None or eng.dtype != x.dtype:
         return None
-    return _Runner(eng, d)
+    plan = DispatchPlan.from_critical(crit)
+    need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in layer.parameters()))
+    try:
+        bufs = eng.acquire(plan.C, hold=need_grad)
+    except RuntimeError:
+        bufs = None
+    if bufs is None:
+        if not eng.warned:
+            import logging
+            logging.warning('tutel_b200: symmetric heap too small for the fused MoE buffers of this layer (C=%d); using the '
+                            'generic all-to-all path. Raise TUTEL_B200_HEAP_MB to enable the fused engine.', plan.C)
+            eng.warned = True
+        return None
+    return _Runner(eng, d, plan, bufs)
 
 
 class _Runner:
-    def __init__(self, eng: FusedEngine, d: int):
-        self.eng, self.d = eng, d
+    def __init__(self, eng: FusedEngine, d: int, plan: DispatchPlan, bufs: _BufferSet):
+        self.eng, self.d, self.plan, self.bufs = eng, d, plan, bufs
 
     def run(self, layer, x: torch.Tensor, crit) -> torch.Tensor:
-        eng = self.eng
-        plan = DispatchPlan.from_critical(crit)
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in layer.parameters()))
-        bufs = eng.acquire(plan.C, hold=need_grad)
-        if bufs is None:
-            raise RuntimeError('tutel_b200: symmetric heap too small for the fused MoE buffers; raise TUTEL_B200_HEAP_MB '
-                               'or set TUTEL_B200_FUSED=0')
+        eng, plan, bufs = self.eng, self.plan, self.bufs
         ex = layer.experts
         gates = crit.gates_ks if hasattr(crit, 'gates_ks') else torch.stack([g.view(-1) for g in crit[3]])
         return _FusedMoE.apply(eng, bufs, plan, self.d, layer.is_postscore, x, gates, ex.batched_fc1_w,
@@ -277,7 +284,9 @@ class _FusedMoE(torch.autograd.Function):
 
         # (c) dh = (dy @ W2^T) * relu'(act)   as rows arrive
         cg, bnh, _ = eng.tile_counts(C, H)
-        dh = G.raw_gemm(dy_recv, w2, epilogue=G.EPI_RELU_BWD, aux=act, b_group_div=W, cta_group=cg, block_n=bnh,
+        want_db1 = ctx.has_b1 and ctx.needs_input_grad[8]
+        db1_acc = torch.zeros([El, H], dtype=torch.float32, device=dout.device) if want_db1 else None
+        dh = G.raw_gemm(dy_recv, w2, epilogue=G.EPI_RELU_BWD, aux=act, b_group_div=W, cta_group=cg, block_n=bnh, colsum=db1_acc,
                         wait_flags=base + bufs.b_disp, wait_rows_per_flag=chunk, wait_flags_per_group=_FLAGS_PER_SEG,
                         wait_target=bufs.epoch, group_rot=rank, group_mod=-W)
 
@@ -296,7 +305,7 @@ class _FusedMoE(torch.autograd.Function):
         act_e, dh_e = act.view(El, W * C, H), dh.view(El, W * C, H)
         dw2 = G.raw_gemm(act_e, dy_recv.view(El, W * C, Mo), a_mn=True, b_mn=True) if ctx.needs_input_grad[9] else None
         dw1 = G.raw_gemm(dh_e, x_recv.view(El, W * C, M), a_mn=True, b_mn=True) if ctx.needs_input_grad[7] else None
-        db1 = dh_e.sum(dim=1, dtype=torch.float32).to(dh.dtype) if ctx.has_b1 and ctx.needs_input_grad[8] else None
+        db1 = db1_acc.to(dh.dtype) if want_db1 else None
         db2 = (dy_recv.view(El, W * C, Mo).sum(dim=1, dtype=torch.float32).to(dh.dtype)
                if ctx.has_b2 and ctx.needs_input_grad[10] else None)
 

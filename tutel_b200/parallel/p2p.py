@@ -8,8 +8,9 @@ exchange the IPC handles.
 
 Layout of the arena::
 
-    [0, 64 KiB)                       counters: 16 slots x 3 arrays (ready / done / barrier) + MoE layer counters
-    [64 KiB, 64 KiB + stage_bytes)    staging region shared by the generic collectives below
+    [0, 4 MiB)                        counters: [0,16K) 64 slots x 4 arrays (ready / done / barrier / scratch),
+                                      [16K, 4M) per-layer MoE arrival flags
+    [4 MiB, 4 MiB + stage_bytes)      staging region shared by the generic collectives below
     [.. , heap_bytes)                 bump-allocated persistent buffers (MoE dispatch / combine buffers)
 """
 from __future__ import annotations
@@ -24,7 +25,7 @@ import torch.distributed as dist
 
 from ..ops import backend
 
-_CTRL_BYTES = 64 << 10
+_CTRL_BYTES = 4 << 20
 _TRANSPORTS: Dict[int, Optional['P2PTransport']] = {}
 _MAX_PEERS = 16
 
@@ -86,7 +87,7 @@ class P2PTransport:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.device = torch.cuda.current_device()
-        heap_mb = int(os.environ.get('TUTEL_B200_HEAP_MB', 3072))
+        heap_mb = int(os.environ.get('TUTEL_B200_HEAP_MB', 8192))
         stage_mb = int(os.environ.get('TUTEL_B200_STAGE_MB', 1280))
         self.heap_bytes = heap_mb << 20
         self.stage_off = _CTRL_BYTES
@@ -131,7 +132,7 @@ class P2PTransport:
         return s
 
     def ctrl_alloc(self, name: str, nbytes: int) -> int:
-        """Zero-initialised counter storage inside the control page area [16 KiB, 64 KiB)."""
+        """Zero-initialised counter storage inside the control area [16 KiB, 4 MiB)."""
         key = '__ctrl__' + name
         if key in self._named:
             return self._named[key][0]
