@@ -2,7 +2,8 @@
 // for the reference's grouped ncclSend/ncclRecv all-to-alls (tutel/custom/custom_kernel.cpp:463-518, 520-654)
 // and c10d all_to_all_single (tutel/impls/communicate.py:181-192).  One launch = handshake + payload + completion:
 //
-//   1. every rank grants its peers a "receive region free" credit   (red.release.sys on the peer's ready[])
+//   1. every rank posts, in each peer's mailbox, WHERE in its arena this call's data must land (epoch | offset/256,
+//      one st.release.sys.u64) - receive buffers are therefore chosen per call and per rank (zero-copy results)
 //   2. CTAs push their share of the payload with 16-byte stores into the destination GPU's heap
 //   3. each CTA publishes completion with fence.acq_rel.sys + red.release.sys on the peer's done[] counter
 //   4. the kernel does not exit before all of its own inbound pushes are complete (ld.acquire.sys polling with a
@@ -22,7 +23,7 @@ constexpr int kPushThreads = 512;
 
 __global__ void __launch_bounds__(kPushThreads)
 p2p_push_kernel(const uint8_t* __restrict__ src, const PushPlan plan, const unsigned long long* __restrict__ peer_table,
-                long long dst_heap_off, long long ready_off, long long done_off, long long scratch_off, int rank,
+                long long recv_heap_off, long long mail_off, long long done_off, long long scratch_off, int rank,
                 int world, uint32_t epoch, int blocks_per_peer) {
   const int pi = blockIdx.x / blocks_per_peer;           // which peer (rotated so that traffic is spread)
   const int sub = blockIdx.x - pi * blocks_per_peer;     // which slice of that peer's payload
@@ -30,14 +31,20 @@ p2p_push_kernel(const uint8_t* __restrict__ src, const PushPlan plan, const unsi
   uint8_t* peer_base = reinterpret_cast<uint8_t*>(peer_table[peer]);
   uint8_t* my_base = reinterpret_cast<uint8_t*>(peer_table[rank]);
 
-  // (1) credits: "rank's receive region for this epoch may be written"
+  // (1) mailboxes: tell every peer where this rank receives this call's data (also the "buffer is free" credit)
   if (blockIdx.x == 0 && threadIdx.x < world) {
     uint8_t* pb = reinterpret_cast<uint8_t*>(peer_table[threadIdx.x]);
-    ptx::red_add_release_sys(reinterpret_cast<uint32_t*>(pb + ready_off) + rank, 1u);
+    const unsigned long long word = (static_cast<unsigned long long>(epoch) << 32) |
+                                    static_cast<unsigned long long>(recv_heap_off >> 8);
+    ptx::st_release_sys_u64(reinterpret_cast<unsigned long long*>(pb + mail_off) + rank, word);
   }
-  // (2) wait for the destination's credit, then push
-  if (threadIdx.x == 0) ptx::wait_flag_ge_sys(reinterpret_cast<const uint32_t*>(my_base + ready_off) + peer, epoch);
+  // (2) wait for the destination's mailbox entry, then push
+  __shared__ unsigned long long dst_heap_off_s;
+  if (threadIdx.x == 0)
+    dst_heap_off_s = static_cast<unsigned long long>(ptx::wait_mailbox_sys(
+                         reinterpret_cast<const unsigned long long*>(my_base + mail_off) + peer, epoch)) << 8;
   __syncthreads();
+  const long long dst_heap_off = static_cast<long long>(dst_heap_off_s);
 
   const long long total = plan.bytes[peer];
   const uint8_t* s = src + plan.src_off[peer];
@@ -127,13 +134,13 @@ __global__ void p2p_barrier_kernel(const unsigned long long* __restrict__ peer_t
 }  // namespace
 
 cudaError_t p2p_push(const void* src, const PushPlan& plan, const unsigned long long* peer_table,
-                     long long dst_heap_off, long long ready_off, long long done_off, long long scratch_off, int rank,
+                     long long recv_heap_off, long long mail_off, long long done_off, long long scratch_off, int rank,
                      int world, uint32_t epoch, int blocks_per_peer, cudaStream_t stream) {
   if (world > kMaxPeers) return cudaErrorInvalidValue;
   if (blocks_per_peer < 1) blocks_per_peer = 1;
   const int grid = world * blocks_per_peer;
-  p2p_push_kernel<<<grid, kPushThreads, 0, stream>>>(static_cast<const uint8_t*>(src), plan, peer_table, dst_heap_off,
-                                                     ready_off, done_off, scratch_off, rank, world, epoch, blocks_per_peer);
+  p2p_push_kernel<<<grid, kPushThreads, 0, stream>>>(static_cast<const uint8_t*>(src), plan, peer_table, recv_heap_off,
+                                                     mail_off, done_off, scratch_off, rank, world, epoch, blocks_per_peer);
   return cudaGetLastError();
 }
 

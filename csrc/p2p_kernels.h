@@ -10,7 +10,8 @@ constexpr int kMaxPeers = 16;
 
 struct PushPlan {
   // For every destination peer p: copy `bytes[p]` bytes from local `src + src_off[p]` to
-  // peer_table[p] + dst_heap_off + dst_off[p].   All offsets/sizes are multiples of 16 bytes... or not:
+  // peer_table[p] + recv_off(p) + dst_off[p], where recv_off(p) is the receive-buffer offset peer p announced for this
+  // call through the mailbox (multiple of 256 bytes).   All offsets/sizes are multiples of 16 bytes... or not:
   // unaligned tails are handled with byte copies.
   long long src_off[kMaxPeers];
   long long dst_off[kMaxPeers];
@@ -18,12 +19,13 @@ struct PushPlan {
 };
 
 // Counters (uint32, inside the heap, zero-initialised, monotonically increasing):
-//   ready[W] at heap offset ready_off: ready[src] on rank d counts "d's receive region is free" credits that d
-//             granted to src.  done[W] at done_off: done[src] on rank d counts finished pushes of src into d.
+//   mail[W] (uint64) at heap offset mail_off: mail[src] on rank d = (epoch << 32 | recv_offset / 256) posted by src:
+//             "for call `epoch`, push my data to this offset of my arena".   done[W] (uint32) at done_off: done[src]
+//             on rank d counts finished pushes of src into d.
 //   scratch[W] at scratch_off: LOCAL block-arrival counters used to elect the last block per destination.
 // `epoch` is the 1-based call number on this (ready, done) counter pair.
 cudaError_t p2p_push(const void* src, const PushPlan& plan, const unsigned long long* peer_table,
-                     long long dst_heap_off, long long ready_off, long long done_off, long long scratch_off, int rank,
+                     long long recv_heap_off, long long mail_off, long long done_off, long long scratch_off, int rank,
                      int world, uint32_t epoch, int blocks_per_peer, cudaStream_t stream);
 
 // out[i] = sum_p peer_p[stage_off + slice_off + i]  for i in [0, n)   (one-shot pull-reduce; fp32 accumulate).

@@ -121,6 +121,31 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
 __device__ __forceinline__ void red_add_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Mailbox word = (epoch << 32) | payload.  Spin until the epoch field reaches `epoch`; returns the payload.
+__device__ __forceinline__ uint32_t wait_mailbox_sys(const unsigned long long* p, uint32_t epoch) {
+  unsigned long long v = ld_acquire_sys_u64(p);
+  if (static_cast<int32_t>(static_cast<uint32_t>(v >> 32) - epoch) >= 0) return static_cast<uint32_t>(v);
+  const uint64_t t0 = globaltimer_ns();
+  for (;;) {
+    __nanosleep(64);
+    v = ld_acquire_sys_u64(p);
+    if (static_cast<int32_t>(static_cast<uint32_t>(v >> 32) - epoch) >= 0) return static_cast<uint32_t>(v);
+    if (globaltimer_ns() - t0 > TB_SPIN_TIMEOUT_NS) {
+      printf("[tutel_b200] peer mailbox wait timeout: block %d mailbox %p have epoch %u want %u\n", blockIdx.x, p,
+             static_cast<uint32_t>(v >> 32), epoch);
+      __trap();
+    }
+  }
+}
+
 // Spin until *p >= target (monotonic epoch counters; wrap-safe signed compare). Traps on timeout.
 __device__ __forceinline__ void wait_flag_ge_sys(const uint32_t* p, uint32_t target) {
   if (static_cast<int32_t>(ld_acquire_sys(p) - target) >= 0) return;

@@ -66,6 +66,50 @@ void SymmHeap::open_peers(int rank, const std::vector<std::string>& handles) {
   TB_CUDA_OK(cudaDeviceSynchronize());
 }
 
+void SymmHeap::set_pool(long long off, long long bytes) {
+  std::lock_guard<std::mutex> g(pool_mu_);
+  pool_free_.clear();
+  pool_used_.clear();
+  if (bytes > 0) pool_free_[off] = bytes;
+}
+
+long long SymmHeap::pool_alloc(long long bytes) {
+  bytes = (bytes + 255) / 256 * 256;
+  if (bytes <= 0) bytes = 256;
+  std::lock_guard<std::mutex> g(pool_mu_);
+  for (auto it = pool_free_.begin(); it != pool_free_.end(); ++it) {
+    if (it->second >= bytes) {
+      const long long off = it->first, len = it->second;
+      pool_free_.erase(it);
+      if (len > bytes) pool_free_[off + bytes] = len - bytes;
+      pool_used_[off] = bytes;
+      return off;
+    }
+  }
+  return -1;
+}
+
+void SymmHeap::pool_free(long long off) {
+  std::lock_guard<std::mutex> g(pool_mu_);
+  auto u = pool_used_.find(off);
+  if (u == pool_used_.end()) return;
+  long long len = u->second;
+  pool_used_.erase(u);
+  auto next = pool_free_.lower_bound(off);
+  if (next != pool_free_.end() && off + len == next->first) {   // merge with the following free block
+    len += next->second;
+    next = pool_free_.erase(next);
+  }
+  if (next != pool_free_.begin()) {                              // merge with the preceding free block
+    auto prev = std::prev(next);
+    if (prev->first + prev->second == off) {
+      prev->second += len;
+      return;
+    }
+  }
+  pool_free_[off] = len;
+}
+
 void SymmHeap::close() {
   if (closed_) return;
   closed_ = true;
@@ -114,6 +158,7 @@ void register_symm_bindings(pybind11::module& m) {
              h.open_peers(static_cast<int>(rank), hs);
            })
       .def("close", &tb::SymmHeap::close)
+      .def("set_pool", [](tb::SymmHeap& h, int64_t off, int64_t bytes) { h.set_pool(off, bytes); })
       .def("bytes", [](const tb::SymmHeap& h) { return static_cast<int64_t>(h.bytes()); })
       .def("world", &tb::SymmHeap::world)
       .def("rank", &tb::SymmHeap::rank)
@@ -128,7 +173,37 @@ void register_symm_bindings(pybind11::module& m) {
              return at::from_blob(p, sizes, [h](void*) {}, opts);
            });
 
-  // src: any local CUDA tensor (bytes view); per-peer byte offsets/sizes as python lists.
+  // One-call collective: allocate the receive buffer from the arena pool (or use the bounce region), announce it to
+  // the peers through the mailboxes, push this rank's payload, and return the received data as a tensor that lives
+  // in the arena (its deleter frees the pool block).  `src_off/dst_off/nbytes` are per-peer byte offsets/sizes.
+  m.def("p2p_collective", [](std::shared_ptr<tb::SymmHeap> h, const at::Tensor& src, std::vector<int64_t> src_off,
+                             std::vector<int64_t> dst_off, std::vector<int64_t> nbytes, std::vector<int64_t> out_sizes,
+                             int64_t slot_off, int64_t epoch, int64_t blocks_per_peer, int64_t bounce_off,
+                             int64_t bounce_bytes) {
+    TORCH_CHECK(src.is_cuda() && src.is_contiguous());
+    const int world = h->world(), rank = h->rank();
+    TORCH_CHECK(world <= tb::kMaxPeers && (int)src_off.size() == world && (int)dst_off.size() == world && (int)nbytes.size() == world);
+    const c10::cuda::CUDAGuard guard(src.device());
+    int64_t out_elems = 1;
+    for (auto v : out_sizes) out_elems *= v;
+    const int64_t out_bytes = out_elems * static_cast<int64_t>(src.element_size());
+    long long off = h->pool_alloc(out_bytes);
+    const bool pooled = off >= 0;
+    if (!pooled) {
+      TORCH_CHECK(out_bytes <= bounce_bytes, "tutel_b200: P2P receive buffer does not fit the arena");
+      off = bounce_off;
+    }
+    tb::PushPlan plan{};
+    for (int p = 0; p < world; ++p) { plan.src_off[p] = src_off[p]; plan.dst_off[p] = dst_off[p]; plan.bytes[p] = nbytes[p]; }
+    TB_CHECK_CUDA(tb::p2p_push(src.data_ptr(), plan, h->device_peer_table(), off, slot_off, slot_off + 128, slot_off + 256,
+                               rank, world, static_cast<uint32_t>(epoch), static_cast<int>(blocks_per_peer), cur_stream()));
+    uint8_t* ptr = static_cast<uint8_t*>(h->base(rank)) + off;
+    auto opts = src.options();
+    if (pooled) {
+      return at::from_blob(ptr, out_sizes, [h, off](void*) { h->pool_free(off); }, opts);
+    }
+    return at::from_blob(ptr, out_sizes, [h](void*) {}, opts).clone();
+  });
   m.def("p2p_push", [](const at::Tensor& src, std::vector<int64_t> src_off, std::vector<int64_t> dst_off,
                        std::vector<int64_t> nbytes, int64_t peer_table, int64_t dst_heap_off, int64_t ready_off,
                        int64_t done_off, int64_t scratch_off, int64_t rank, int64_t world, int64_t epoch,

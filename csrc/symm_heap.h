@@ -4,6 +4,8 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -26,6 +28,12 @@ class SymmHeap {
   void* base(int r) const { return peer_base_.at(r); }
   const unsigned long long* device_peer_table() const { return d_peer_table_; }
 
+  // Receive-buffer pool inside the arena (first-fit free list, 256-byte granularity).  Collectives allocate their
+  // output here and hand it out as a tensor whose deleter returns the block - no copy out of a staging area.
+  void set_pool(long long off, long long bytes);
+  long long pool_alloc(long long bytes);   // -1 when no block fits
+  void pool_free(long long off);
+
  private:
   size_t bytes_ = 0;
   int device_ = 0;
@@ -34,6 +42,9 @@ class SymmHeap {
   std::vector<void*> peer_base_;
   unsigned long long* d_peer_table_ = nullptr;
   bool closed_ = false;
+  std::mutex pool_mu_;
+  std::map<long long, long long> pool_free_;   // offset -> length of free blocks
+  std::map<long long, long long> pool_used_;   // offset -> length of live blocks
 };
 
 }  // namespace tb

@@ -51,11 +51,12 @@ def _start_exchange(packed: torch.Tensor, group, pending: _Pending) -> None:
         side = _comm_stream(packed.device)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            out = t.all_to_all(packed, copy=True)
+            out = t.all_to_all(packed)
             ev = torch.cuda.Event()
             ev.record(side)
         packed.record_stream(side)
-        out.record_stream(cur)
+        # `out` lives in the transport's arena pool: its block is only re-used by a later collective, which is ordered
+        # after everything queued on the consumer stream (wait_stream above)
         pending.out, pending.wait = out, (lambda: torch.cuda.current_stream().wait_event(ev))
     elif packed.is_cuda:
         out = torch.empty_like(packed)

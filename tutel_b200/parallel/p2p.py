@@ -87,21 +87,24 @@ class P2PTransport:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.device = torch.cuda.current_device()
-        heap_mb = int(os.environ.get('TUTEL_B200_HEAP_MB', 8192))
-        stage_mb = int(os.environ.get('TUTEL_B200_STAGE_MB', 1280))
+        heap_mb = int(os.environ.get('TUTEL_B200_HEAP_MB', 12288))
+        stage_mb = int(os.environ.get('TUTEL_B200_STAGE_MB', 4096))
         self.heap_bytes = heap_mb << 20
         self.stage_off = _CTRL_BYTES
         self.stage_bytes = min(stage_mb << 20, self.heap_bytes // 2)
         self._bump = self.stage_off + self.stage_bytes
+        # staging = [bounce region for reductions / pool overflow | receive-buffer pool of the push collectives]
+        self.bounce_bytes = self.stage_bytes // 4
         self.heap = _C.SymmHeap(self.heap_bytes, self.device)
         handles = [None] * self.world
         dist.all_gather_object(handles, self.heap.ipc_handle(), group=group)
         self.heap.open_peers(self.rank, handles)
         dist.barrier(group=group)
         self.peer_table = self.heap.peer_table_ptr()
+        self.heap.set_pool(self.stage_off + self.bounce_bytes, self.stage_bytes - self.bounce_bytes)
         self._C = _C
-        # counter slots: slot s -> ready at 256*s, done at 256*s+64, barrier at 256*s+128, local scratch at 256*s+192
-        # (uint32[16] each)
+        # counter slots (512 B each): mailboxes uint64[16] at +0, done uint32[16] at +128, barrier at +192, local scratch
+        # at +256
         self._epochs: Dict[int, int] = {}
         self._named: Dict[str, tuple] = {}
         self._next_slot = 2  # slot 0: generic push, slot 1: generic barrier/reduce
@@ -127,7 +130,7 @@ class P2PTransport:
     def new_counter_slot(self) -> int:
         s = self._next_slot
         self._next_slot += 1
-        if 256 * (s + 1) > 16 << 10:
+        if 512 * (s + 1) > 16 << 10:
             raise RuntimeError('tutel_b200: out of counter slots')
         return s
 
@@ -163,7 +166,7 @@ class P2PTransport:
 
     # ---- primitives -----------------------------------------------------------------------------------------
     def barrier(self, slot: int = 1) -> None:
-        self._C.p2p_barrier(self.peer_table, 256 * slot + 128, self.rank, self.world, self._next_epoch(('b', slot)))
+        self._C.p2p_barrier(self.peer_table, 512 * slot + 192, self.rank, self.world, self._next_epoch(('b', slot)))
 
     def _blocks_per_peer(self, max_bytes: int) -> int:
         if max_bytes <= (64 << 10):
@@ -172,15 +175,19 @@ class P2PTransport:
             return 4
         return max(8, min(74, 592 // self.world))     # ~4 CTAs per SM in total: enough bytes in flight for NVLink
 
-    def push(self, src: torch.Tensor, src_off: List[int], dst_off: List[int], nbytes: List[int], dst_heap_off: int,
-             slot: int = 0) -> None:
-        self._C.p2p_push(src, src_off, dst_off, nbytes, self.peer_table, dst_heap_off, 256 * slot, 256 * slot + 64,
-                         256 * slot + 192, self.rank, self.world, self._next_epoch(slot),
-                         self._blocks_per_peer(max(nbytes)))
+    def collective(self, src: torch.Tensor, src_off: List[int], dst_off: List[int], nbytes: List[int], out_shape,
+                   slot: int = 0) -> torch.Tensor:
+        """Push-based collective with a zero-copy result: the receive buffer is taken from the arena pool, announced
+        to the peers per call, and returned as a tensor (freed back to the pool when the tensor dies)."""
+        return self._C.p2p_collective(self.heap, src, src_off, dst_off, nbytes, list(out_shape), 512 * slot,
+                                      self._next_epoch(slot), self._blocks_per_peer(max(nbytes)), self.stage_off,
+                                      self.bounce_bytes)
 
     # ---- generic collectives (staging region; results are copied out so that callers may keep them) -------------
     def fits(self, nbytes: int) -> bool:
-        return nbytes <= self.stage_bytes
+        # a rank whose pool is momentarily full receives into the bounce region (and copies out), so the size test
+        # that every rank evaluates identically is against the bounce region
+        return nbytes <= self.bounce_bytes
 
     def all_to_all(self, x: torch.Tensor, copy: bool = True) -> torch.Tensor:
         nbytes = x.numel() * x.element_size()
@@ -189,10 +196,8 @@ class P2PTransport:
             dist.all_to_all_single(out, x, group=self.group)
             return out
         chunk = nbytes // self.world
-        self.push(x, [p * chunk for p in range(self.world)], [self.rank * chunk] * self.world, [chunk] * self.world,
-                  self.stage_off)
-        out = self.view(self.stage_off, x.shape, x.dtype)
-        return out.clone() if copy else out
+        return self.collective(x, [p * chunk for p in range(self.world)], [self.rank * chunk] * self.world,
+                               [chunk] * self.world, x.shape)
 
     def all_gather(self, x: torch.Tensor) -> torch.Tensor:
         nbytes = x.numel() * x.element_size()
@@ -200,8 +205,8 @@ class P2PTransport:
             out = torch.empty([self.world * x.numel()], device=x.device, dtype=x.dtype)
             dist.all_gather_into_tensor(out, x.view(-1), group=self.group)
             return out
-        self.push(x, [0] * self.world, [self.rank * nbytes] * self.world, [nbytes] * self.world, self.stage_off)
-        return self.view(self.stage_off, [self.world * x.numel()], x.dtype).clone()
+        return self.collective(x, [0] * self.world, [self.rank * nbytes] * self.world, [nbytes] * self.world,
+                               [self.world * x.numel()])
 
     def all_gather_v(self, x: torch.Tensor, sizes: List[int]) -> torch.Tensor:
         es = x.element_size()
@@ -215,8 +220,7 @@ class P2PTransport:
             return torch.cat([p[:n] for p, n in zip(pieces, sizes)])
         my_off = sum(sizes[: self.rank]) * es
         n = sizes[self.rank] * es
-        self.push(x, [0] * self.world, [my_off] * self.world, [n] * self.world, self.stage_off)
-        return self.view(self.stage_off, [sum(sizes)], x.dtype).clone()
+        return self.collective(x, [0] * self.world, [my_off] * self.world, [n] * self.world, [sum(sizes)])
 
     def all_to_all_v(self, x: torch.Tensor, matrix: List[List[int]]) -> torch.Tensor:
         """``matrix[s][d]`` = elements rank s sends to rank d (known to every rank)."""
@@ -234,11 +238,10 @@ class P2PTransport:
             src_off.append(acc * es)
             acc += n
         dst_off = [sum(matrix[s][d] for s in range(self.rank)) * es for d in range(self.world)]
-        self.push(x, src_off, dst_off, [n * es for n in in_list], self.stage_off)
-        return self.view(self.stage_off, [sum(out_list)], x.dtype).clone()
+        return self.collective(x, src_off, dst_off, [n * es for n in in_list], [sum(out_list)])
 
     # ---- reductions: one-shot pull over NVLink for small tensors --------------------------------------------------
-    _REDUCE_MAX_BYTES = 4 << 20
+    _REDUCE_MAX_BYTES = 4 << 20     # must stay below bounce_bytes
 
     def supports_reduce(self, x: torch.Tensor, op) -> bool:
         return (x.dtype in (torch.float32, torch.float16, torch.bfloat16) and op in (dist.ReduceOp.SUM, dist.ReduceOp.MAX)
