@@ -41,6 +41,7 @@ def gemm_cases():
     cases.append(dict(kind='gemm', M=16384, N=4096, K=14336, G=1, a_mn=False, b_mn=True, cg=2, bn=256, perf=True))
     cases.append(dict(kind='gemm', M=14336, N=4096, K=16384, G=1, a_mn=True, b_mn=True, cg=2, bn=256, perf=True))
     cases.append(dict(kind='gemm', M=8192, N=8192, K=8192, G=1, a_mn=False, b_mn=False, cg=2, bn=256, perf=True))
+    cases.append(dict(kind='gemm', M=4096, N=14336, K=2048, G=8, a_mn=True, b_mn=True, cg=2, bn=256, perf=True))   # per-expert wgrad, short K
     cases.append(dict(kind='gemm', M=8192, N=8192, K=8192, G=1, a_mn=False, b_mn=False, cg=1, bn=256, perf=True))
     cases.append(dict(kind='fp8', M=16384, N=14336, K=4096, G=1, cg=2))
     cases.append(dict(kind='fp8', M=16384, N=4096, K=14336, G=1, cg=2))

@@ -12,21 +12,27 @@ import torch
 import torch.nn.functional as F
 from torch.profiler import ProfilerActivity, profile
 
-from tutel_b200 import moe, net, system
-
 ap = argparse.ArgumentParser()
 ap.add_argument('--out', type=str, default=os.path.join(ROOT, 'gpurun_out', 'step_profile.txt'))
 ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--experts', type=int, default=8)
+ap.add_argument('--expert_type', type=str, default='ffn')
+ap.add_argument('--overlap', type=int, default=1)
+ap.add_argument('--reference', action='store_true', help='profile the unmodified reference (baseline/_ref) instead')
 args = ap.parse_args()
+if args.reference:
+    sys.path.insert(0, os.path.join(ROOT, 'baseline', '_ref'))
+    from tutel import moe, net, system
+else:
+    from tutel_b200 import moe, net, system
 
 env = system.init_data_model_parallel(backend='nccl')
 rank, world, dev = env.global_rank, env.global_size, env.local_device
 torch.set_default_dtype(torch.bfloat16)
 layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2, 'capacity_factor': 1.0}, model_dim=4096,
-                      experts={'type': 'ffn', 'num_experts_per_device': args.experts // world, 'hidden_size_per_expert': 14336,
+                      experts={'type': args.expert_type, 'num_experts_per_device': args.experts // world, 'hidden_size_per_expert': 14336,
                                'activation_fn': lambda x: F.relu(x)},
-                      scan_expert_func=lambda n, p: setattr(p, 'skip_allreduce', True), seeds=(1, rank + 1, 1)).to(dev)
+                      scan_expert_func=lambda n, p: setattr(p, 'skip_allreduce', True), seeds=(1, rank + 1, 1), a2a_ffn_overlap_degree=args.overlap).to(dev)
 opt = torch.optim.SGD(layer.parameters(), lr=1e-5)
 shared = [p for p in layer.parameters() if not hasattr(p, 'skip_allreduce')]
 torch.manual_seed(rank)

@@ -244,6 +244,74 @@ std::vector<at::Tensor> quantize_rows(const at::Tensor& x) {
   return {q, scale};
 }
 
+// Gated-linear-unit GEMMs (SwiGLU / GeGLU / ReGLU experts; reference: tutel/experts/llama_ffn.py:38-41 runs three
+// cuBLAS GEMMs plus separate activation and multiply kernels).
+//   forward  (b2 given):  h = act(a*b) .* (a*b2)   [+ g = a*b -> d2, u = a*b2 -> d3 when given]   ONE launch
+//   backward (aux given): acc = a*b (= dh);  d = dh .* u .* act'(g),  d2 = dh .* act(g)   with g = aux, u = aux2
+void gemm_glu(const at::Tensor& a, const at::Tensor& b, const c10::optional<at::Tensor>& b2, at::Tensor& d,
+              const c10::optional<at::Tensor>& d2, const c10::optional<at::Tensor>& d3,
+              const c10::optional<at::Tensor>& aux, const c10::optional<at::Tensor>& aux2, bool b_mn, int64_t act,
+              const c10::optional<at::Tensor>& scale_a, const c10::optional<at::Tensor>& scale_b,
+              const c10::optional<at::Tensor>& scale_b2, const c10::optional<at::Tensor>& row_counts) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && d.is_cuda() && a.dim() == 3 && b.dim() == 3 && d.dim() == 3);
+  TORCH_CHECK(a.stride(2) == 1 && b.stride(2) == 1 && d.stride(2) == 1 && a.scalar_type() == b.scalar_type());
+  const c10::cuda::CUDAGuard guard(a.device());
+  const bool fwd = b2.has_value() && b2->defined();
+  tb::GemmProblem p;
+  p.G = static_cast<int>(a.size(0));
+  p.M = static_cast<int>(a.size(1));
+  p.K = static_cast<int>(a.size(2));
+  p.N = static_cast<int>(b_mn ? b.size(2) : b.size(1));
+  TORCH_CHECK((b_mn ? b.size(1) : b.size(2)) == p.K, "tutel_b200.gemm_glu: K mismatch");
+  TORCH_CHECK(b.size(0) == p.G && d.size(0) == p.G && d.size(1) == p.M && d.size(2) == p.N && d.element_size() == 2);
+  p.a = a.data_ptr(); p.lda = a.stride(1); p.a_group_stride = a.stride(0);
+  p.b = b.data_ptr(); p.ldb = b.stride(1); p.b_group_stride = b.stride(0); p.b_mn_major = b_mn;
+  p.in_dtype = gemm_dtype_of(a);
+  p.d = d.data_ptr(); p.ldd = d.stride(1); p.d_group_stride = d.stride(0);
+  p.out_dtype = gemm_dtype_of(d);
+  p.act = static_cast<int>(act);
+  auto same_as_d = [&](const at::Tensor& t) {
+    return t.is_cuda() && t.scalar_type() == d.scalar_type() && t.sizes() == d.sizes() && t.strides() == d.strides();
+  };
+  if (fwd) {
+    TORCH_CHECK(b2->scalar_type() == b.scalar_type() && b2->sizes() == b.sizes() && b2->strides() == b.strides(),
+                "tutel_b200.gemm_glu: b2 must have the layout of b");
+    p.epilogue = tb::EPI_GLU;
+    p.b2 = b2->data_ptr();
+    if (d2.has_value() && d2->defined()) {
+      TORCH_CHECK(d3.has_value() && d3->defined() && same_as_d(*d2) && same_as_d(*d3), "tutel_b200.gemm_glu: d2/d3 must look like d");
+      p.d2 = d2->data_ptr();
+      p.d3 = d3->data_ptr();
+    }
+  } else {
+    TORCH_CHECK(aux.has_value() && aux2.has_value() && d2.has_value() && same_as_d(*d2) && same_as_d(*aux) &&
+                    aux2->scalar_type() == d.scalar_type() && aux2->sizes() == aux->sizes() && aux2->strides() == aux->strides(),
+                "tutel_b200.gemm_glu: backward needs aux, aux2 and d2 shaped like d");
+    p.epilogue = tb::EPI_GLU_BWD;
+    p.aux = aux->data_ptr(); p.ld_aux = aux->stride(1); p.aux_group_stride = aux->stride(0);
+    p.aux2 = aux2->data_ptr();
+    p.d2 = d2->data_ptr();
+  }
+  auto scale = [&](const c10::optional<at::Tensor>& t, int64_t cols, const float** ptr, long long* stride) {
+    if (!t.has_value() || !t->defined()) return;
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kFloat && t->dim() == 2 && t->stride(1) == 1 && t->size(1) == cols);
+    *ptr = t->data_ptr<float>();
+    if (stride) *stride = t->stride(0);
+  };
+  scale(scale_a, p.M, &p.scale_a, &p.scale_a_group_stride);
+  scale(scale_b, p.N, &p.scale_b, &p.scale_b_group_stride);
+  long long s2 = p.scale_b_group_stride;
+  scale(scale_b2, p.N, &p.scale_b2, &s2);
+  TORCH_CHECK(s2 == p.scale_b_group_stride, "tutel_b200.gemm_glu: scale_b / scale_b2 stride mismatch");
+  if (row_counts.has_value() && row_counts->defined()) {
+    TORCH_CHECK(row_counts->is_cuda() && row_counts->scalar_type() == at::kInt && row_counts->numel() >= p.G);
+    p.row_counts = row_counts->data_ptr<int>();
+  }
+  const char* why = nullptr;
+  cudaError_t e = tb::gemm_sm100_launch(p, cur_stream(), &why);
+  TORCH_CHECK(e == cudaSuccess, "tutel_b200.gemm_glu launch failed: ", why ? why : cudaGetErrorString(e));
+}
+
 at::Tensor skinny_gemm(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias,
                        const c10::optional<at::Tensor>& counts, bool w_is_kn, bool relu) {
   TORCH_CHECK(x.is_cuda() && w.is_cuda() && x.dim() == 3 && w.dim() == 3 && x.is_contiguous() && w.is_contiguous());
@@ -278,6 +346,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "tutel_b200 native runtime: sm_100a tcgen05 grouped GEMM, routing/dispatch kernels, symmetric heap, "
             "P2P collectives, NVRTC JIT";
   m.def("gemm", &gemm);
+  m.def("gemm_glu", &gemm_glu);
   m.def("route_locations", &route_locations);
   m.def("build_slot_map", &build_slot_map);
   m.def("encode_rows", &encode_rows);

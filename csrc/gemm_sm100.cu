@@ -53,6 +53,12 @@ struct GemmArgs {
   int bias_is_bf16;
   const void* aux;
   long long ld_aux, aux_group_stride;
+  const void* aux2;
+  void* d2;
+  void* d3;
+  int dual;        // EPI_GLU: B tile = 128 columns of tmB + the same 128 columns of tmB2
+  int act;
+  const float* scale_b2;
 
   const int* row_counts;
   float* colsum;  // [G / b_group_div, N] fp32: += column sums of the epilogue result (bias gradient), may be null
@@ -67,6 +73,7 @@ struct GemmArgs {
   uint32_t wait_target;
   const unsigned long long* signal_ptr_table;
   int staged_store;  // 16-bit outputs: stage rows in smem and write them with cp.async.bulk (full 64 B segments)
+  int tma_store;     // 16-bit local outputs: stage 32x32 blocks in smem and write them with ONE tensor store each
   int group_rot, group_mod;  // tile order visits group (g/mod)*mod + (g%mod + rot)%mod  (own-rank segment first)
 };
 
@@ -85,9 +92,17 @@ struct Cfg {
   static constexpr int A_BYTES = BM_CTA * kSwizzleBytes;
   static constexpr int B_BYTES = BN_CTA * kSwizzleBytes;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  // Epilogue staging, 8 KB per epilogue warp, used in one of two ways:
+  //  - local outputs: 4 slots of 32 rows x 64 B in the TMA SWIZZLE_64B layout, one tensor store per slot;
+  //  - remote outputs (per-group pointer table): 3 slots of 32 padded rows, one bulk store per row.
   static constexpr int EPI_ROW_BYTES = 80;                       // 64 B of payload + 16 B pad (bank-conflict free)
   static constexpr int EPI_SLOT_BYTES = 32 * EPI_ROW_BYTES;      // one warp, one 32-column chunk
-  static constexpr int EPI_BYTES = 4 * 2 * EPI_SLOT_BYTES;       // 4 epilogue warps, double buffered
+  static constexpr int EPI_ROW_SLOTS = 3;
+  static constexpr int EPI_TMA_SLOT_BYTES = 32 * 64;
+  static constexpr int EPI_TMA_SLOTS = 4;
+  static constexpr int EPI_WARP_BYTES = 8192;
+  static_assert(EPI_ROW_SLOTS * EPI_SLOT_BYTES <= EPI_WARP_BYTES && EPI_TMA_SLOTS * EPI_TMA_SLOT_BYTES <= EPI_WARP_BYTES, "");
+  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
   static constexpr int AUX_BYTES = 1024 /*align slack*/ + 512 /*barriers + tmem ptr*/ + EPI_BYTES;
   static constexpr int STAGES_RAW = (kSmemLimit - AUX_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -163,6 +178,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, bool is_bf16) {
 template <int CG, bool A_MN, bool B_MN, int BN, int ELT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmD,
+                  const __grid_constant__ CUtensorMap tmD2, const __grid_constant__ CUtensorMap tmD3,
                   const GemmArgs args) {
   using C = Cfg<CG, BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -189,6 +206,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
+    if (args.dual) ptx::prefetch_tensormap(&tmB2);
+    if (args.tma_store) ptx::prefetch_tensormap(&tmD);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -214,6 +233,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const long long tile_step = gridDim.x / CG;
   const long long tile_first = blockIdx.x / CG;
   constexpr int kBand = (CG == 2) ? 8 : 16;
+  const bool dual = args.dual != 0;
+  const int tile_n = dual ? BN / 2 : BN;   // output columns per tile
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -226,7 +247,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc.g = rotate_group(tc.g, args.group_rot, args.group_mod);
       if (args.row_counts != nullptr && tc.m_blk * C::BM >= args.row_counts[tc.g]) continue;
       const int m0 = tc.m_blk * C::BM + static_cast<int>(cta_rank) * C::BM_CTA;
-      const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * C::BN_CTA;
+      const int n0 = tc.n_blk * BN + static_cast<int>(cta_rank) * C::BN_CTA;   // (non-dual) first B column of this CTA
       const int gb = tc.g / args.b_group_div;
       if (args.wait_flags != nullptr) {
         // Dispatch fusion: rows of this tile are pushed by peer GPUs; acquire their release flags - once per
@@ -274,18 +295,45 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
           // ---- B ----
-          if constexpr (!B_MN) {
-            if constexpr (CG == 1) ptx::tma_load_3d(smem_b(s), &tmB, fb, k0, n0, gb);
-            else ptx::tma_load_3d_2sm(smem_b(s), &tmB, fb, k0, n0, gb);
+          if (!dual) {
+            if constexpr (!B_MN) {
+              if constexpr (CG == 1) ptx::tma_load_3d(smem_b(s), &tmB, fb, k0, n0, gb);
+              else ptx::tma_load_3d_2sm(smem_b(s), &tmB, fb, k0, n0, gb);
+            } else {
+              constexpr int chunk_elems = kSwizzleBytes / kEltBytes;
+              const int chunk_bytes = bk_elems * kSwizzleBytes;
+              const int nchunk = C::BN_CTA / chunk_elems;
+              for (int c = 0; c < nchunk; ++c) {
+                if constexpr (CG == 1)
+                  ptx::tma_load_3d(smem_b(s) + c * chunk_bytes, &tmB, fb, n0 + c * chunk_elems, k0, gb);
+                else
+                  ptx::tma_load_3d_2sm(smem_b(s) + c * chunk_bytes, &tmB, fb, n0 + c * chunk_elems, k0, gb);
+              }
+            }
           } else {
-            constexpr int chunk_elems = kSwizzleBytes / kEltBytes;
-            const int chunk_bytes = bk_elems * kSwizzleBytes;
-            const int nchunk = C::BN_CTA / chunk_elems;
-            for (int c = 0; c < nchunk; ++c) {
-              if constexpr (CG == 1)
-                ptx::tma_load_3d(smem_b(s) + c * chunk_bytes, &tmB, fb, n0 + c * chunk_elems, k0, gb);
-              else
-                ptx::tma_load_3d_2sm(smem_b(s) + c * chunk_bytes, &tmB, fb, n0 + c * chunk_elems, k0, gb);
+            // GLU: accumulator columns [0, BN/2) come from B, [BN/2, BN) from B2, both at weight columns nb0...
+            // A CTA pair splits exactly there: rank 0 stages the B tile, rank 1 the B2 tile.
+            const int nb0 = tc.n_blk * (BN / 2);
+            if constexpr (!B_MN) {
+              if constexpr (CG == 1) {
+                ptx::tma_load_3d(smem_b(s), &tmB, fb, k0, nb0, gb);
+                ptx::tma_load_3d(smem_b(s) + (BN / 2) * kSwizzleBytes, &tmB2, fb, k0, nb0, gb);
+              } else {
+                ptx::tma_load_3d_2sm(smem_b(s), cta_rank ? &tmB2 : &tmB, fb, k0, nb0, gb);
+              }
+            } else {
+              constexpr int chunk_elems = kSwizzleBytes / kEltBytes;
+              const int chunk_bytes = bk_elems * kSwizzleBytes;
+              constexpr int half_chunks = (BN / 2) / chunk_elems;
+              if constexpr (CG == 1) {
+                for (int c = 0; c < 2 * half_chunks; ++c)
+                  ptx::tma_load_3d(smem_b(s) + c * chunk_bytes, c < half_chunks ? &tmB : &tmB2, fb,
+                                   nb0 + (c % half_chunks) * chunk_elems, k0, gb);
+              } else {
+                for (int c = 0; c < half_chunks; ++c)
+                  ptx::tma_load_3d_2sm(smem_b(s) + c * chunk_bytes, cta_rank ? &tmB2 : &tmB, fb,
+                                       nb0 + c * chunk_elems, k0, gb);
+              }
             }
           }
         }
@@ -350,7 +398,15 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t acc_ph = 0;
     const bool out16 = (args.out_dtype != DT_FP32);
     const bool out_bf16 = (args.out_dtype == DT_BF16);
-    const bool staged = out16 && args.staged_store != 0;
+    const bool glu = args.epilogue == EPI_GLU || args.epilogue == EPI_GLU_BWD;
+    // Output paths: (1) local 16-bit: 32x32 blocks through swizzled smem and one tensor store per block;
+    // (2) remote (NVLink) 16-bit: padded smem rows and one bulk store per row (full 64-byte segments on the wire; the
+    // copy engine retires only ~50 of these small operations per microsecond and SM, fine for one output per
+    // accumulator);  (3) straight from registers (fp32, row_counts tails, TUTEL_B200_EPI=direct).
+    const bool tma_out = out16 && args.tma_store != 0;
+    const bool staged = out16 && args.staged_store != 0 && !tma_out && !glu;
+    const uint32_t epi_warp = epi_base + static_cast<uint32_t>(ew) * C::EPI_WARP_BYTES;
+    int slot_toggle = 0;
     for (long long t = tile_first; t < args.num_tiles; t += tile_step) {
       TileCoord tc = decode_tile<kBand>(t, args.tiles_m, args.tiles_n);
       tc.g = rotate_group(tc.g, args.group_rot, args.group_mod);
@@ -379,6 +435,180 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ptx::mbar_wait(tfull_bar(acc), acc_ph);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(ew * 32) << 16);
+
+      // One 32-column segment of this thread's row -> global memory (16-bit: via a padded smem row and one bulk
+      // store per row segment, or direct 16-byte stores; fp32: direct).
+      const int m_warp0 = tc.m_blk * C::BM + static_cast<int>(cta_rank) * C::BM_CTA + ew * 32;
+      auto store_seg = [&](const CUtensorMap* tm, uint8_t* row, int n, int ncols, const float* v) {
+        if (tma_out) {
+          const uint32_t slot = epi_warp + static_cast<uint32_t>(slot_toggle) * C::EPI_TMA_SLOT_BYTES;
+          slot_toggle = (slot_toggle + 1) & (C::EPI_TMA_SLOTS - 1);
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");  // the store that used this slot has read it
+          __syncwarp();
+          const uint32_t my = slot + static_cast<uint32_t>(lane) * 64u;
+          const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;               // SWIZZLE_64B: 16-byte unit ^= row/2 % 4
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t o0 = pack2(v[q * 8 + 0], v[q * 8 + 1], out_bf16), o1 = pack2(v[q * 8 + 2], v[q * 8 + 3], out_bf16);
+            const uint32_t o2 = pack2(v[q * 8 + 4], v[q * 8 + 5], out_bf16), o3 = pack2(v[q * 8 + 6], v[q * 8 + 7], out_bf16);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(my + ((static_cast<uint32_t>(q) ^ sw) << 4)), "r"(o0),
+                         "r"(o1), "r"(o2), "r"(o3)
+                         : "memory");
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (m_warp0 < args.M) ptx::tma_store_3d(tm, slot, n, m_warp0, tc.g);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else if (staged) {
+          const uint32_t slot = epi_warp + static_cast<uint32_t>(slot_toggle) * C::EPI_SLOT_BYTES +
+                                static_cast<uint32_t>(lane) * C::EPI_ROW_BYTES;
+          slot_toggle = slot_toggle == C::EPI_ROW_SLOTS - 1 ? 0 : slot_toggle + 1;
+          asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");  // the bulk store that used this slot has read it
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t o0 = pack2(v[q * 8 + 0], v[q * 8 + 1], out_bf16), o1 = pack2(v[q * 8 + 2], v[q * 8 + 3], out_bf16);
+            const uint32_t o2 = pack2(v[q * 8 + 4], v[q * 8 + 5], out_bf16), o3 = pack2(v[q * 8 + 6], v[q * 8 + 7], out_bf16);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + q * 16), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
+                         : "memory");
+          }
+          ptx::fence_proxy_async_smem();
+          if (row_ok)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(row + n * 2), "r"(slot),
+                         "r"(static_cast<uint32_t>(ncols * 2))
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        } else if (row_ok) {
+          if (out16) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q * 8 < ncols) {
+                uint4 o;
+                o.x = pack2(v[q * 8 + 0], v[q * 8 + 1], out_bf16);
+                o.y = pack2(v[q * 8 + 2], v[q * 8 + 3], out_bf16);
+                o.z = pack2(v[q * 8 + 4], v[q * 8 + 5], out_bf16);
+                o.w = pack2(v[q * 8 + 6], v[q * 8 + 7], out_bf16);
+                *reinterpret_cast<uint4*>(row + (n + q * 8) * 2) = o;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (q * 4 < ncols) {
+                float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                *reinterpret_cast<float4*>(row + (n + q * 4) * 4) = o;
+              }
+            }
+          }
+        }
+      };
+      // 32 values of a 16-bit [.., ld] side input (zeros for rows past the end)
+      auto load_seg16 = [&](const uint8_t* row, int n, int ncols, float* f) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (row_ok && q * 8 < ncols) {
+            unpack8(ptx::ld_nc_v4(row + (n + q * 8) * 2), out_bf16, f + q * 8);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[q * 8 + j] = 0.0f;
+          }
+        }
+      };
+
+      if (glu) {
+        // ---------------- gated-linear-unit epilogues ----------------
+        const bool fwd = args.epilogue == EPI_GLU;
+        const long long row_off = (static_cast<long long>(tc.g) * args.d_group_stride + static_cast<long long>(m) * args.ldd) * 2;
+        uint8_t* d2_row = args.d2 != nullptr ? reinterpret_cast<uint8_t*>(args.d2) + row_off : nullptr;
+        uint8_t* d3_row = args.d3 != nullptr ? reinterpret_cast<uint8_t*>(args.d3) + row_off : nullptr;
+        const uint8_t* aux2_row = nullptr;
+        if (args.aux2 != nullptr)
+          aux2_row = reinterpret_cast<const uint8_t*>(args.aux2) +
+                     (static_cast<long long>(tc.g) * args.aux_group_stride + static_cast<long long>(m) * args.ld_aux) * 2;
+        const float sa = (args.scale_a != nullptr && row_ok)
+                             ? args.scale_a[static_cast<long long>(tc.g) * args.scale_a_group_stride + m] : 1.0f;
+        // packed side inputs of the NEXT segment are fetched while the current one is computed (backward only)
+        uint4 pg[4], pu[4];
+        auto fetch_side = [&](int n, int ncols) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (row_ok && q * 8 < ncols) {
+              pg[q] = ptx::ld_nc_v4(aux_row + (n + q * 8) * 2);
+              pu[q] = ptx::ld_nc_v4(aux2_row + (n + q * 8) * 2);
+            } else {
+              pg[q] = make_uint4(0u, 0u, 0u, 0u);
+              pu[q] = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+        };
+        if (!fwd && tc.n_blk * tile_n < args.N) fetch_side(tc.n_blk * tile_n, min(32, args.N - tc.n_blk * tile_n));
+#pragma unroll 1
+        for (int c = 0; c < tile_n / 32; ++c) {
+          const int n = tc.n_blk * tile_n + c * 32;
+          if (n >= args.N) break;  // warp-uniform
+          const int ncols = min(32, args.N - n);
+          uint32_t r[32];
+          float g[32], u[32], o[32];
+          ptx::tmem_ld_32x32(t_row + static_cast<uint32_t>(c * 32), r);
+          ptx::tmem_ld_wait();
+          if (fwd) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(r[j]);
+            ptx::tmem_ld_32x32(t_row + static_cast<uint32_t>(BN / 2 + c * 32), r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) u[j] = __uint_as_float(r[j]);
+            if (args.scale_a != nullptr || args.scale_b != nullptr) {
+              const float* sb = args.scale_b != nullptr ? args.scale_b + static_cast<long long>(gb) * args.scale_b_group_stride + n : nullptr;
+              const float* sb2 = args.scale_b2 != nullptr ? args.scale_b2 + static_cast<long long>(gb) * args.scale_b_group_stride + n : nullptr;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                g[j] *= (sb != nullptr && j < ncols) ? sa * sb[j] : sa;
+                u[j] *= (sb2 != nullptr && j < ncols) ? sa * sb2[j] : sa;
+              }
+            }
+            if (d2_row != nullptr) {       // training: keep the pre-activations for the backward pass
+              store_seg(&tmD2, d2_row, n, ncols, g);
+              store_seg(&tmD3, d3_row, n, ncols, u);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float a = args.act == ACT_RELU ? fmaxf(g[j], 0.0f) : (args.act == ACT_GELU ? gelu_erf(g[j]) : silu(g[j]));
+              o[j] = a * u[j];
+            }
+            store_seg(&tmD, d_row, n, ncols, o);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              unpack8(pg[q], out_bf16, g + q * 8);
+              unpack8(pu[q], out_bf16, u + q * 8);
+            }
+            if (c + 1 < tile_n / 32 && n + 32 < args.N) fetch_side(n + 32, min(32, args.N - n - 32));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float dh = __uint_as_float(r[j]);
+              float a, da;
+              if (args.act == ACT_RELU) {
+                a = fmaxf(g[j], 0.0f);
+                da = g[j] > 0.0f ? 1.0f : 0.0f;
+              } else if (args.act == ACT_GELU) {
+                const float cdf = 0.5f * (1.0f + erff(g[j] * 0.70710678118654752f));
+                a = g[j] * cdf;
+                da = cdf + g[j] * 0.3989422804014327f * __expf(-0.5f * g[j] * g[j]);
+              } else {
+                const float sg = 1.0f / (1.0f + __expf(-g[j]));
+                a = g[j] * sg;
+                da = sg * (1.0f + g[j] * (1.0f - sg));
+              }
+              o[j] = dh * u[j] * da;   // d gate
+              u[j] = dh * a;           // d up
+            }
+            store_seg(&tmD, d_row, n, ncols, o);
+            store_seg(&tmD2, d2_row, n, ncols, u);
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int n = tc.n_blk * BN + c * 32;
@@ -404,17 +634,15 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= args.alpha;
           }
-        } else if (args.epilogue == EPI_RELU_BWD) {
-          if (row_ok) {
+        } else if (args.epilogue == EPI_RELU_BWD || args.epilogue == EPI_ADD) {
+          float f[32];
+          load_seg16(aux_row, n, ncols, f);
+          if (args.epilogue == EPI_RELU_BWD) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (q * 8 < ncols) {
-                float f[8];
-                unpack8(ptx::ld_nc_v4(aux_row + (n + q * 8) * 2), out_bf16, f);
+            for (int j = 0; j < 32; ++j) v[j] = f[j] > 0.0f ? v[j] : 0.0f;
+          } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[q * 8 + j] = f[j] > 0.0f ? v[q * 8 + j] : 0.0f;
-              }
-            }
+            for (int j = 0; j < 32; ++j) v[j] += f[j];
           }
         } else {
           if (bias_g != nullptr) {
@@ -466,47 +694,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (lane < ncols)
             atomicAdd(args.colsum + static_cast<long long>(gb) * args.colsum_group_stride + n + lane, s[0]);
         }
-        if (staged) {
-          // registers -> padded smem row (this thread's own) -> one asynchronous bulk store of the row segment
-          const uint32_t slot = epi_base + static_cast<uint32_t>(ew * 2 + (c & 1)) * C::EPI_SLOT_BYTES +
-                                static_cast<uint32_t>(lane) * C::EPI_ROW_BYTES;
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the bulk store that used this slot has read it
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t o0 = pack2(v[q * 8 + 0], v[q * 8 + 1], out_bf16), o1 = pack2(v[q * 8 + 2], v[q * 8 + 3], out_bf16);
-            const uint32_t o2 = pack2(v[q * 8 + 4], v[q * 8 + 5], out_bf16), o3 = pack2(v[q * 8 + 6], v[q * 8 + 7], out_bf16);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + q * 16), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
-                         : "memory");
-          }
-          ptx::fence_proxy_async_smem();
-          if (row_ok)
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(d_row + n * 2), "r"(slot),
-                         "r"(static_cast<uint32_t>(ncols * 2))
-                         : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        } else if (row_ok) {
-          if (out16) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (q * 8 < ncols) {
-                uint4 o;
-                o.x = pack2(v[q * 8 + 0], v[q * 8 + 1], out_bf16);
-                o.y = pack2(v[q * 8 + 2], v[q * 8 + 3], out_bf16);
-                o.z = pack2(v[q * 8 + 4], v[q * 8 + 5], out_bf16);
-                o.w = pack2(v[q * 8 + 6], v[q * 8 + 7], out_bf16);
-                *reinterpret_cast<uint4*>(d_row + (n + q * 8) * 2) = o;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              if (q * 4 < ncols) {
-                float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                *reinterpret_cast<float4*>(d_row + (n + q * 4) * 4) = o;
-              }
-            }
-          }
-        }
+        store_seg(&tmD, d_row, n, ncols, v);
+      }
       }
       // Accumulator drained: hand the TMEM buffer back to the MMA warp.
       ptx::tc_fence_before();
@@ -590,6 +779,24 @@ bool make_operand_map(CUtensorMap* map, const void* base, int dtype, bool mn_maj
   return true;
 }
 
+// 16-bit output [G, M, N] viewed in 32-column x 32-row blocks, SWIZZLE_64B (the layout the epilogue warps write).
+bool make_output_map(CUtensorMap* map, const void* base, int dtype, long long rows, long long cols, long long ld,
+                     long long group_stride, int groups, const char** why) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) { *why = "cuTensorMapEncodeTiled unavailable"; return false; }
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(groups)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2,
+                           static_cast<cuuint64_t>(groups > 1 ? group_stride : rows * ld) * 2};
+  if (strides[1] == 0) strides[1] = strides[0];
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { *why = "cuTensorMapEncodeTiled (output) failed"; return false; }
+  return true;
+}
+
 uint32_t make_idesc(int in_dtype, bool a_mn, bool b_mn, int umma_m, int umma_n) {
   uint32_t fmt;
   switch (in_dtype) {
@@ -609,9 +816,13 @@ uint32_t make_idesc(int in_dtype, bool a_mn, bool b_mn, int umma_m, int umma_n) 
   return d;
 }
 
+struct OutMaps {
+  CUtensorMap d, d2, d3;
+};
+
 template <int CG, bool A_MN, bool B_MN, int BN, int ELT>
-cudaError_t launch_inst(const CUtensorMap& ta, const CUtensorMap& tb_, const GemmArgs& args, int grid,
-                        cudaStream_t stream) {
+cudaError_t launch_inst(const CUtensorMap& ta, const CUtensorMap& tb_, const CUtensorMap& tb2, const OutMaps& om,
+                        const GemmArgs& args, int grid, cudaStream_t stream) {
   using C = Cfg<CG, BN>;
   auto* kern = gemm_sm100_kernel<CG, A_MN, B_MN, BN, ELT>;
   static bool configured = false;
@@ -632,7 +843,7 @@ cudaError_t launch_inst(const CUtensorMap& ta, const CUtensorMap& tb_, const Gem
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, ta, tb_, args);
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb_, tb2, om.d, om.d2, om.d3, args);
 }
 
 }  // namespace
@@ -657,9 +868,17 @@ cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const c
   int sms = sm_count_cache[dev & 63];
   if (p.max_ctas > 0) sms = p.max_ctas < sms ? p.max_ctas : sms;
 
+  const bool dual = p.epilogue == EPI_GLU;
+  if (dual && (p.b2 == nullptr || p.out_dtype == DT_FP32)) { *why = "EPI_GLU needs b2 and a 16-bit output"; return cudaErrorInvalidValue; }
+  if (p.epilogue == EPI_GLU_BWD && (p.aux == nullptr || p.aux2 == nullptr || p.d2 == nullptr || p.out_dtype == DT_FP32)) {
+    *why = "EPI_GLU_BWD needs aux, aux2, d2 and a 16-bit output";
+    return cudaErrorInvalidValue;
+  }
+  if ((p.epilogue == EPI_GLU || p.epilogue == EPI_GLU_BWD) && p.d_ptr_table != nullptr) { *why = "GLU epilogues write local outputs only"; return cudaErrorInvalidValue; }
   int cg = p.cta_group;
   int bn = p.block_n;
-  if (bn == 0) bn = (p.N <= 128) ? 128 : 256;
+  if (bn == 0) bn = (p.N <= 128 && !dual) ? 128 : 256;
+  if (dual) bn = 256;
   if (cg == 0) cg = (p.M > 128) ? 2 : 1;
   if (cg == 2 && (sms & 1)) sms -= 1;
 
@@ -668,7 +887,7 @@ cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const c
   a.M = p.M; a.N = p.N; a.K = p.K; a.G = p.G;
   a.b_group_div = p.b_group_div > 0 ? p.b_group_div : 1;
   a.tiles_m = (p.M + bm - 1) / bm;
-  a.tiles_n = (p.N + bn - 1) / bn;
+  a.tiles_n = dual ? (p.N + bn / 2 - 1) / (bn / 2) : (p.N + bn - 1) / bn;
   a.num_tiles = static_cast<long long>(a.tiles_m) * a.tiles_n * p.G;
   a.idesc = make_idesc(p.in_dtype, p.a_mn_major, p.b_mn_major, bm, bn);
   a.elt_bytes = eb;
@@ -678,6 +897,7 @@ cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const c
   a.bias = p.bias; a.bias_group_stride = p.bias_group_stride; a.bias_is_fp32 = 0;
   a.bias_is_bf16 = (eb == 2) ? (p.in_dtype == DT_BF16) : (p.out_dtype == DT_BF16);
   a.aux = p.aux; a.ld_aux = p.ld_aux; a.aux_group_stride = p.aux_group_stride;
+  a.aux2 = p.aux2; a.d2 = p.d2; a.d3 = p.d3; a.dual = dual ? 1 : 0; a.act = p.act; a.scale_b2 = p.scale_b2;
   a.row_counts = p.row_counts;
   a.colsum = p.colsum; a.colsum_group_stride = p.colsum_group_stride;
   a.scale_a = p.scale_a; a.scale_a_group_stride = p.scale_a_group_stride;
@@ -699,14 +919,31 @@ cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const c
   const int gB = (p.G + a.b_group_div - 1) / a.b_group_div;
   if (!make_operand_map(&ta, p.a, p.in_dtype, p.a_mn_major, p.M, p.K, p.lda, p.a_group_stride, p.G, 128, why))
     return cudaErrorInvalidValue;
-  if (!make_operand_map(&tb_, p.b, p.in_dtype, p.b_mn_major, p.N, p.K, p.ldb, p.b_group_stride, gB, bn / cg, why))
+  const int b_box = dual ? bn / 2 : bn / cg;
+  if (!make_operand_map(&tb_, p.b, p.in_dtype, p.b_mn_major, p.N, p.K, p.ldb, p.b_group_stride, gB, b_box, why))
     return cudaErrorInvalidValue;
+  CUtensorMap tb2 = tb_;
+  if (dual && !make_operand_map(&tb2, p.b2, p.in_dtype, p.b_mn_major, p.N, p.K, p.ldb, p.b_group_stride, gB, b_box, why))
+    return cudaErrorInvalidValue;
+
+  // Local 16-bit outputs leave through tensor stores (one per 32x32 block).
+  OutMaps om;
+  om.d = ta; om.d2 = ta; om.d3 = ta;   // placeholders (never dereferenced unless tma_store is set)
+  a.tma_store = 0;
+  if (a.staged_store && p.out_dtype != DT_FP32 && p.d_ptr_table == nullptr && p.row_counts == nullptr && p.d != nullptr) {
+    if (!make_output_map(&om.d, p.d, p.out_dtype, p.M, p.N, p.ldd, p.d_group_stride, p.G, why)) return cudaErrorInvalidValue;
+    if (p.d2 != nullptr && !make_output_map(&om.d2, p.d2, p.out_dtype, p.M, p.N, p.ldd, p.d_group_stride, p.G, why))
+      return cudaErrorInvalidValue;
+    if (p.d3 != nullptr && !make_output_map(&om.d3, p.d3, p.out_dtype, p.M, p.N, p.ldd, p.d_group_stride, p.G, why))
+      return cudaErrorInvalidValue;
+    a.tma_store = 1;
+  }
 
   long long want = a.num_tiles * cg;
   int grid = static_cast<int>(want < sms ? want : sms);
   if (cg == 2 && (grid & 1)) grid += 1;
 
-#define TB_LAUNCH(CGv, AMN, BMN, BNv) return launch_inst<CGv, AMN, BMN, BNv, 2>(ta, tb_, a, grid, stream)
+#define TB_LAUNCH(CGv, AMN, BMN, BNv) return launch_inst<CGv, AMN, BMN, BNv, 2>(ta, tb_, tb2, om, a, grid, stream)
 #define TB_SWITCH_MAJOR(CGv, BNv)                                    \
   do {                                                               \
     if (!p.a_mn_major && !p.b_mn_major) TB_LAUNCH(CGv, false, false, BNv); \
@@ -716,10 +953,10 @@ cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const c
   } while (0)
   if (eb == 1) {
     if (p.a_mn_major || p.b_mn_major) { *why = "fp8 operands must be K-major"; return cudaErrorInvalidValue; }
-    if (cg == 1 && bn == 256) return launch_inst<1, false, false, 256, 1>(ta, tb_, a, grid, stream);
-    if (cg == 1 && bn == 128) return launch_inst<1, false, false, 128, 1>(ta, tb_, a, grid, stream);
-    if (cg == 2 && bn == 256) return launch_inst<2, false, false, 256, 1>(ta, tb_, a, grid, stream);
-    if (cg == 2 && bn == 128) return launch_inst<2, false, false, 128, 1>(ta, tb_, a, grid, stream);
+    if (cg == 1 && bn == 256) return launch_inst<1, false, false, 256, 1>(ta, tb_, tb2, om, a, grid, stream);
+    if (cg == 1 && bn == 128) return launch_inst<1, false, false, 128, 1>(ta, tb_, tb2, om, a, grid, stream);
+    if (cg == 2 && bn == 256) return launch_inst<2, false, false, 256, 1>(ta, tb_, tb2, om, a, grid, stream);
+    if (cg == 2 && bn == 128) return launch_inst<2, false, false, 128, 1>(ta, tb_, tb2, om, a, grid, stream);
   }
   if (cg == 1 && bn == 256) TB_SWITCH_MAJOR(1, 256);
   if (cg == 1 && bn == 128) TB_SWITCH_MAJOR(1, 128);

@@ -12,7 +12,12 @@ enum GemmEpilogue : int {
   EPI_BIAS_GELU = 3,  // D = gelu_erf(acc + bias[n])
   EPI_BIAS_SILU = 4,  // D = silu(acc + bias[n])
   EPI_RELU_BWD = 5,   // D = aux[m,n] > 0 ? acc : 0     (aux = forward activation output)
+  EPI_GLU = 6,        // dual-B: D = act(A*B) .* (A*B2); optionally also stores g = A*B -> d2 and u = A*B2 -> d3
+  EPI_GLU_BWD = 7,    // acc = dh:  D = dh * u * act'(g)  and  d2 = dh * act(g)   with g = aux, u = aux2
+  EPI_ADD = 8,        // D = acc + aux[m,n]
 };
+
+enum GemmAct : int { ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3 };
 
 enum GemmDtype : int { DT_BF16 = 0, DT_FP16 = 1, DT_FP32 = 2, DT_E4M3 = 3, DT_E5M2 = 4 };
 
@@ -32,6 +37,11 @@ struct GemmProblem {
   long long ldb = 0, b_group_stride = 0;
   bool b_mn_major = false;
   int in_dtype = DT_BF16;  // A and B element type
+  // EPI_GLU only: second B operand with the layout / strides of `b`.  One 256-wide accumulator tile then holds 128
+  // columns of A*B ("gate") and the SAME 128 columns of A*B2 ("up"); with CTA pairs each CTA stages one of the two
+  // weight tiles, so the gated activation costs no extra shared-memory traffic and no separate elementwise pass.
+  const void* b2 = nullptr;
+  int act = ACT_SILU;      // activation of EPI_GLU / EPI_GLU_BWD
 
   void* d = nullptr;
   long long ldd = 0, d_group_stride = 0;
@@ -39,6 +49,8 @@ struct GemmProblem {
   // Optional: per-group output base pointers (device array of G uint64). Entries may point into PEER GPUs'
   // memory (NVLink P2P mapping): this is how the GEMM->combine all-to-all is fused into the epilogue.
   const unsigned long long* d_ptr_table = nullptr;
+  void* d2 = nullptr;  // extra outputs of the GLU epilogues (strides / dtype of `d`)
+  void* d3 = nullptr;
 
   int epilogue = EPI_NONE;
   float alpha = 1.0f;
@@ -46,6 +58,7 @@ struct GemmProblem {
   long long bias_group_stride = 0;
   const void* aux = nullptr;  // [G, M, N] row-major, out_dtype
   long long ld_aux = 0, aux_group_stride = 0;
+  const void* aux2 = nullptr;  // EPI_GLU_BWD: the "up" pre-activation (strides of `aux`)
 
   // fp8 (e4m3 / e5m2, K-major) operands: optional per-row scales of A [G, M] and per-column scales of B [G/div, N]
   // (fp32); the epilogue computes D = acc * scale_a[m] * scale_b[n] before bias / activation.
@@ -53,6 +66,7 @@ struct GemmProblem {
   long long scale_a_group_stride = 0;
   const float* scale_b = nullptr;
   long long scale_b_group_stride = 0;
+  const float* scale_b2 = nullptr;  // column scales of b2 (stride of scale_b)
 
   // Optional: fp32 [G/div, N] accumulator that receives (atomically) the column sums of the stored result - the bias
   // gradient of the layer, fused into the dgrad GEMM instead of a separate reduction pass.  Must be zeroed by the caller.

@@ -206,6 +206,13 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t smem_dst, const void* t
       : "memory");
 }
 
+// Tensor store smem -> global (bulk async group of the issuing thread); out-of-range rows / columns are clipped.
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, loads
 // ----------------------------------------------------------------------------------------------

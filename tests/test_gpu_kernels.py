@@ -252,3 +252,75 @@ def test_fp8_forward_layer_close_to_bf16():
     ya.float().pow(2).mean().backward()
     yb.float().pow(2).mean().backward()
     assert (xb.grad.float() - xa.grad.float()).norm() / xa.grad.float().norm() < 0.15
+
+
+def _act(name, t):
+    return {'relu': torch.relu, 'silu': F.silu, 'gelu': F.gelu}[name](t)
+
+
+@pytest.mark.parametrize('act', ['silu', 'relu', 'gelu'])
+@pytest.mark.parametrize('M,b_mn', [(96, True), (328, True), (328, False), (1000, True)])
+def test_glu_dual_b_gemm_forward_and_backward_epilogues(C, act, M, b_mn):
+    """h = act(x@W1) * (x@W2) from ONE launch (gate/up halves share a TMEM tile), and the dh GEMM that emits dg/du."""
+    from tutel_b200.ops import gemm as G
+    torch.manual_seed(3)
+    Gn, K, N = 2, 264, 328          # N not a multiple of the 128-column half tile
+    x = (torch.randn(Gn, M, K, device='cuda') * 0.5).bfloat16()
+    w1 = (torch.randn(Gn, K, N, device='cuda') * 0.1).bfloat16()
+    w2 = (torch.randn(Gn, K, N, device='cuda') * 0.1).bfloat16()
+    b1 = w1 if b_mn else w1.transpose(1, 2).contiguous()
+    b2 = w2 if b_mn else w2.transpose(1, 2).contiguous()
+    h, g, u = G.glu_gemm(x, b1, b2, b_mn=b_mn, act=act, save_pre=True)
+    g_ref, u_ref = x.float() @ w1.float(), x.float() @ w2.float()
+    assert torch.allclose(g.float(), g_ref, atol=0.05, rtol=2e-2)
+    assert torch.allclose(u.float(), u_ref, atol=0.05, rtol=2e-2)
+    assert torch.allclose(h.float(), _act(act, g_ref) * u_ref, atol=0.05, rtol=3e-2)
+    h_only, _, _ = G.glu_gemm(x, b1, b2, b_mn=b_mn, act=act)
+    assert torch.equal(h_only, h)
+
+    # backward epilogue: dh = dy @ W3^T stays in TMEM, the epilogue writes dg and du
+    Mo = 136
+    dy = (torch.randn(Gn, M, Mo, device='cuda') * 0.5).bfloat16()
+    w3 = (torch.randn(Gn, N, Mo, device='cuda') * 0.1).bfloat16()
+    dg, du = G.glu_gemm_bwd(dy, w3, g, u, b_mn=False, act=act)
+    gf = g.float().requires_grad_(True)
+    uf = u.float().requires_grad_(True)
+    dh = dy.float() @ w3.float().transpose(1, 2)
+    (_act(act, gf) * uf).backward(dh)
+    assert torch.allclose(dg.float(), gf.grad, atol=0.05, rtol=3e-2)
+    assert torch.allclose(du.float(), uf.grad, atol=0.05, rtol=3e-2)
+
+
+def test_gemm_add_epilogue(C):
+    torch.manual_seed(4)
+    a = torch.randn(2, 300, 128, device='cuda').bfloat16()
+    b = torch.randn(2, 264, 128, device='cuda').bfloat16()
+    aux = torch.randn(2, 300, 264, device='cuda').bfloat16()
+    d = torch.empty_like(aux)
+    _gemm(C, a, b, d, False, False, epi=8, aux=aux)
+    assert torch.allclose(d.float(), a.float() @ b.float().transpose(1, 2) + aux.float(), atol=0.15, rtol=2e-2)
+
+
+@pytest.mark.parametrize('act', ['silu', 'relu'])
+@pytest.mark.parametrize('fp8', [False, True])
+def test_llama_ffn_expert_fused_glu_matches_autograd(act, fp8):
+    """The llama_ffn expert (reference tutel/experts/llama_ffn.py) through the fused GLU path vs plain fp32 autograd."""
+    from tutel_b200.ops import gemm as G
+    torch.manual_seed(5)
+    Gn, T, M, H = 2, 512, 256, 384
+    x = (torch.randn(Gn, T, M, device='cuda') * 0.5).bfloat16().requires_grad_(True)
+    ws = [(torch.randn(Gn, *s, device='cuda') * 0.05).bfloat16().requires_grad_(True) for s in ((M, H), (M, H), (H, M))]
+    y = G.fused_glu_ffn(x, *ws, act, fp8)
+    dy = (torch.randn_like(y) * 0.1)
+    y.backward(dy)
+    xr = x.detach().float().requires_grad_(True)
+    wr = [w.detach().float().requires_grad_(True) for w in ws]
+    yr = (_act(act, xr @ wr[0]) * (xr @ wr[1])) @ wr[2]
+    yr.backward(dy.float())
+    def rel(a, b):
+        return ((a.float() - b).norm() / b.norm()).item()
+    errs = [rel(y, yr), rel(x.grad, xr.grad)] + [rel(w.grad, r.grad) for w, r in zip(ws, wr)]
+    if fp8:     # e4m3 forward: ~4 % per GEMM; its pre-activations also decide the ReLU mask used in backward
+        assert errs[0] < 0.1 and max(errs) < 0.3, errs
+    else:       # bf16: rounding of the saved activations
+        assert max(errs) < 0.02, errs

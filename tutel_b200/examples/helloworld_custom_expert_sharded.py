@@ -21,7 +21,7 @@ class ShardedLinearExpert(torch.nn.Module):
 
     def forward(self, x, ctx):
         group = net.create_groups_from_world(group_count=-self.sharded_count, parent_group=ctx.group).model_group
-        w = net.zero_gather(self.W, group=group).view(-1).narrow(0, 0, self.full_shape.numel()).view(self.full_shape)
+        w = net.zero_gather(self.W, full_shape=self.full_shape, group=group)
         y = torch.matmul(x, w)
         return self.act(y) if self.act is not None else y
 

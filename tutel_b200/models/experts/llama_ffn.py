@@ -38,12 +38,18 @@ class LlamaFFNNetwork(torch.nn.Module):
     def _full(self, name, parent_group):
         param, shape = getattr(self, name), self.full_shapes[name]
         group = C.create_groups_from_world(group_count=-self.sharded_count, parent_group=parent_group).model_group
-        return C.zero_gather(param, group=group).view(-1).narrow(0, 0, shape.numel()).view(shape)
+        # zero_gather drops the padding of the last shard and reshapes; with one sharer it is a pure view of the
+        # parameter (no copies in either direction)
+        return C.zero_gather(param, full_shape=shape, group=group)
 
     def forward(self, x, ctx):
         w1, w2, w3 = (self._full(n, ctx.group) for n in ('W_fc1', 'W_fc2', 'W_fc3'))
         if x.dim() > 3:
             x = x.reshape(x.size(0), x.size(1), -1)
+        kind = G.classify_activation(self.activation_fn)
+        if kind in G.ACT_CODES and G.can_use_tcgen05(x, w1) and w3.size(-1) % 8 == 0:
+            # gate/up GEMMs + activation + multiply in one dual-B tcgen05 launch; backward without elementwise passes
+            return G.fused_glu_ffn(x, w1, w2, w3, kind, self.fp8 and x.size(-1) % 16 == 0 and w3.size(1) % 16 == 0)
         y1 = G.grouped_linear(x, w1, None, 'kn', fp8=self.fp8)
         y2 = G.grouped_linear(x, w2, None, 'kn', fp8=self.fp8)
         return G.grouped_linear(self.activation_fn(y1) * y2, w3, None, 'kn', fp8=self.fp8)

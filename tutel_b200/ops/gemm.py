@@ -18,6 +18,8 @@ import torch
 from . import backend
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_GELU, EPI_BIAS_SILU, EPI_RELU_BWD = 0, 1, 2, 3, 4, 5
+EPI_GLU, EPI_GLU_BWD, EPI_ADD = 6, 7, 8
+ACT_CODES = {'relu': 1, 'gelu': 2, 'silu': 3}
 
 
 def _ok_stride(t: torch.Tensor) -> bool:
@@ -182,10 +184,12 @@ _PROBE = None
 
 
 def classify_activation(fn) -> Optional[str]:
-    """Recognise ReLU (also when wrapped in a lambda, as the reference examples do) by probing it once."""
+    """Recognise ReLU / SiLU / GELU (also when wrapped in a lambda, as the reference examples do) by probing once."""
     global _PROBE
     if fn is None or fn is torch.relu or fn is torch.nn.functional.relu or isinstance(fn, torch.nn.ReLU):
         return 'relu'
+    if fn is torch.nn.functional.silu or isinstance(fn, torch.nn.SiLU):
+        return 'silu'
     if isinstance(fn, str):
         return fn
     cached = getattr(fn, '_tutel_b200_kind', None)
@@ -197,8 +201,13 @@ def classify_activation(fn) -> Optional[str]:
     try:
         with torch.no_grad():
             a, b = fn(_PROBE.clone()), fn(_PROBE.clone())
-        if isinstance(a, torch.Tensor) and a.shape == _PROBE.shape and torch.equal(a, b) and torch.equal(a, torch.relu(_PROBE)):
-            kind = 'relu'
+        if isinstance(a, torch.Tensor) and a.shape == _PROBE.shape and torch.equal(a, b):
+            if torch.equal(a, torch.relu(_PROBE)):
+                kind = 'relu'
+            elif torch.allclose(a, torch.nn.functional.silu(_PROBE), atol=1e-6, rtol=1e-6):
+                kind = 'silu'
+            elif torch.allclose(a, torch.nn.functional.gelu(_PROBE), atol=1e-6, rtol=1e-6):
+                kind = 'gelu'
     except Exception:  # noqa
         kind = ''
     try:
@@ -275,3 +284,76 @@ def fused_relu_ffn_fp8(x, w1, b1, w2, b2, row_counts=None):
     b1 = None if b1 is None else b1.reshape(w1.size(0), -1)
     b2 = None if b2 is None else b2.reshape(w2.size(0), -1)
     return FusedReluFFNFp8.apply(x, w1, b1, w2, b2, row_counts)
+
+
+def glu_gemm(a, b, b2, *, b_mn, act, save_pre=False, scale_a=None, scale_b=None, scale_b2=None, row_counts=None,
+             out_dtype=None):
+    """h = act(a @ B) * (a @ B2) in ONE tcgen05 launch (each CTA of a pair stages one of the two weight tiles; the
+    gate/up halves meet in the TMEM accumulator).  ``save_pre`` also returns the pre-activations (g, u)."""
+    C = backend.require_ext()
+    a, b, b2 = _prep(a), _prep(b), _prep(b2)
+    if b2.stride() != b.stride():
+        b, b2 = b.contiguous(), b2.contiguous()
+    N = b.size(2) if b_mn else b.size(1)
+    dt = out_dtype or (a.dtype if a.element_size() > 1 else torch.bfloat16)
+    h = torch.empty([a.size(0), a.size(1), N], dtype=dt, device=a.device)
+    g, u = (torch.empty_like(h), torch.empty_like(h)) if save_pre else (None, None)
+    backend.count_launch()
+    C.gemm_glu(a, b, b2, h, g, u, None, None, b_mn, ACT_CODES[act], scale_a, scale_b, scale_b2, row_counts)
+    return h, g, u
+
+
+def glu_gemm_bwd(dy, w, g, u, *, b_mn, act, row_counts=None):
+    """(dg, du) for h = act(g) * u with dh = dy @ W formed in TMEM only (never written to memory)."""
+    C = backend.require_ext()
+    dy, w = _prep(dy), _prep(w)
+    dg, du = torch.empty_like(g), torch.empty_like(g)
+    backend.count_launch()
+    C.gemm_glu(dy, w, None, dg, du, None, g, u, b_mn, ACT_CODES[act], None, None, None, row_counts)
+    return dg, du
+
+
+class FusedGLUFFN(torch.autograd.Function):
+    """y = (act(x @ W1) * (x @ W2)) @ W3 - the SwiGLU / "LLaMA" expert (reference: tutel/experts/llama_ffn.py:38-41,
+    three cuBLAS GEMMs + activation + multiply, and their five autograd kernels in backward).
+
+    Here: 2 launches forward (dual-B GLU GEMM, down projection), 4-6 backward (dh GEMM whose epilogue emits dg and du,
+    three wgrads, optionally two dgrads with the add fused), no elementwise kernels at all.
+    ``w1, w2: [G, M, H]``, ``w3: [G, H, Mout]`` (all "kn", the reference's parameter layout).
+    """
+
+    @staticmethod
+    def forward(ctx: Any, x, w1, w2, w3, act: str, fp8: bool):
+        need_grad = any(ctx.needs_input_grad[:4])
+        if fp8:
+            xq, sx = quantize_rows(x)
+            (q1, s1), (q2, s2), (q3, s3) = fp8_weight(w1, 'kn'), fp8_weight(w2, 'kn'), fp8_weight(w3, 'kn')
+            h, g, u = glu_gemm(xq, q1, q2, b_mn=False, act=act, save_pre=need_grad, scale_a=sx, scale_b=s1, scale_b2=s2,
+                               out_dtype=x.dtype)
+            hq, sh = quantize_rows(h)
+            y = raw_gemm(hq, q3, out_dtype=x.dtype, scale_a=sh, scale_b=s3)
+        else:
+            h, g, u = glu_gemm(x, w1, w2, b_mn=True, act=act, save_pre=need_grad)
+            y = raw_gemm(h, w3, b_mn=True)
+        ctx.act = act
+        if need_grad:
+            ctx.save_for_backward(x, w1, w2, w3, g, u, h)
+        return y
+
+    @staticmethod
+    def backward(ctx: Any, dy: torch.Tensor):
+        x, w1, w2, w3, g, u, h = ctx.saved_tensors
+        dy = dy if _ok_stride(dy) else dy.contiguous()
+        dg, du = glu_gemm_bwd(dy, w3, g, u, b_mn=False, act=ctx.act)        # dh = dy @ W3^T (W3 [H,Mout] is "nk" here)
+        dw3 = raw_gemm(h, dy, a_mn=True, b_mn=True) if ctx.needs_input_grad[3] else None   # [H,Mout] = h^T @ dy
+        dw1 = raw_gemm(x, dg, a_mn=True, b_mn=True) if ctx.needs_input_grad[1] else None   # [M,H] = x^T @ dg
+        dw2 = raw_gemm(x, du, a_mn=True, b_mn=True) if ctx.needs_input_grad[2] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = raw_gemm(dg, w1)                                            # [T,M] = dg @ W1^T
+            dx = raw_gemm(du, w2, epilogue=EPI_ADD, aux=dx)                  # += du @ W2^T (add fused in the epilogue)
+        return dx, dw1, dw2, dw3, None, None
+
+
+def fused_glu_ffn(x, w1, w2, w3, act='silu', fp8=False):
+    return FusedGLUFFN.apply(x, w1, w2, w3, act, fp8)

@@ -511,7 +511,9 @@ def zero_gather(input, full_shape=None, group=None):
     numel = 1
     for v in full_shape:
         numel *= int(v)
-    out = _AllGather.apply(input, True, group)
+    out = _AllGather.apply(input, True, group) if get_world_size(group) > 1 else input
+    if out.numel() == numel:        # no padding: a pure view (a slice would cost a zero-fill + copy in backward)
+        return out.view(full_shape)
     return out.reshape(-1)[:numel].view(full_shape)
 
 
