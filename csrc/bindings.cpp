@@ -252,7 +252,9 @@ void gemm_glu(const at::Tensor& a, const at::Tensor& b, const c10::optional<at::
               const c10::optional<at::Tensor>& d2, const c10::optional<at::Tensor>& d3,
               const c10::optional<at::Tensor>& aux, const c10::optional<at::Tensor>& aux2, bool b_mn, int64_t act,
               const c10::optional<at::Tensor>& scale_a, const c10::optional<at::Tensor>& scale_b,
-              const c10::optional<at::Tensor>& scale_b2, const c10::optional<at::Tensor>& row_counts) {
+              const c10::optional<at::Tensor>& scale_b2, const c10::optional<at::Tensor>& row_counts,
+              int64_t b_group_div, int64_t cta_group, int64_t wait_flags, int64_t wait_rows_per_flag,
+              int64_t wait_flags_per_group, int64_t wait_target, int64_t group_rot, int64_t group_mod) {
   TORCH_CHECK(a.is_cuda() && b.is_cuda() && d.is_cuda() && a.dim() == 3 && b.dim() == 3 && d.dim() == 3);
   TORCH_CHECK(a.stride(2) == 1 && b.stride(2) == 1 && d.stride(2) == 1 && a.scalar_type() == b.scalar_type());
   const c10::cuda::CUDAGuard guard(a.device());
@@ -263,7 +265,15 @@ void gemm_glu(const at::Tensor& a, const at::Tensor& b, const c10::optional<at::
   p.K = static_cast<int>(a.size(2));
   p.N = static_cast<int>(b_mn ? b.size(2) : b.size(1));
   TORCH_CHECK((b_mn ? b.size(1) : b.size(2)) == p.K, "tutel_b200.gemm_glu: K mismatch");
-  TORCH_CHECK(b.size(0) == p.G && d.size(0) == p.G && d.size(1) == p.M && d.size(2) == p.N && d.element_size() == 2);
+  p.b_group_div = static_cast<int>(b_group_div > 0 ? b_group_div : 1);
+  TORCH_CHECK(b.size(0) * p.b_group_div >= p.G && d.size(0) == p.G && d.size(1) == p.M && d.size(2) == p.N && d.element_size() == 2);
+  p.cta_group = static_cast<int>(cta_group);
+  p.wait_flags = reinterpret_cast<const uint32_t*>(wait_flags);
+  p.wait_rows_per_flag = static_cast<int>(wait_rows_per_flag);
+  p.wait_flags_per_group = static_cast<int>(wait_flags_per_group);
+  p.wait_target = static_cast<uint32_t>(wait_target);
+  p.group_rot = static_cast<int>(group_rot);
+  p.group_mod = static_cast<int>(group_mod != 0 ? group_mod : 1);
   p.a = a.data_ptr(); p.lda = a.stride(1); p.a_group_stride = a.stride(0);
   p.b = b.data_ptr(); p.ldb = b.stride(1); p.b_group_stride = b.stride(0); p.b_mn_major = b_mn;
   p.in_dtype = gemm_dtype_of(a);

@@ -74,6 +74,9 @@ struct GemmArgs {
   const unsigned long long* signal_ptr_table;
   int staged_store;  // 16-bit outputs: stage rows in smem and write them with cp.async.bulk (full 64 B segments)
   int tma_store;     // 16-bit local outputs: stage 32x32 blocks in smem and write them with ONE tensor store each
+  int tma_side;      // side inputs (aux / aux2) arrive through tensor loads into swizzled smem, one segment ahead
+  int stages;        // depth of the operand ring
+  int epi_warp_bytes;
   int group_rot, group_mod;  // tile order visits group (g/mod)*mod + (g%mod + rot)%mod  (own-rank segment first)
 };
 
@@ -92,24 +95,29 @@ struct Cfg {
   static constexpr int A_BYTES = BM_CTA * kSwizzleBytes;
   static constexpr int B_BYTES = BN_CTA * kSwizzleBytes;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // Epilogue staging, 8 KB per epilogue warp, used in one of two ways:
-  //  - local outputs: 4 slots of 32 rows x 64 B in the TMA SWIZZLE_64B layout, one tensor store per slot;
+  // Epilogue staging per epilogue warp (the host picks the size per launch and derives the ring depth from it):
+  //  - local outputs: 2 KB slots of 32 rows x 64 B in the TMA SWIZZLE_64B layout, one tensor store per slot
+  //    (4 slots; with side inputs: 2 store slots + 2 stages x 2 side-input slots filled by tensor loads);
   //  - remote outputs (per-group pointer table): 3 slots of 32 padded rows, one bulk store per row.
   static constexpr int EPI_ROW_BYTES = 80;                       // 64 B of payload + 16 B pad (bank-conflict free)
   static constexpr int EPI_SLOT_BYTES = 32 * EPI_ROW_BYTES;      // one warp, one 32-column chunk
   static constexpr int EPI_ROW_SLOTS = 3;
   static constexpr int EPI_TMA_SLOT_BYTES = 32 * 64;
-  static constexpr int EPI_TMA_SLOTS = 4;
   static constexpr int EPI_WARP_BYTES = 8192;
-  static_assert(EPI_ROW_SLOTS * EPI_SLOT_BYTES <= EPI_WARP_BYTES && EPI_TMA_SLOTS * EPI_TMA_SLOT_BYTES <= EPI_WARP_BYTES, "");
-  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
-  static constexpr int AUX_BYTES = 1024 /*align slack*/ + 512 /*barriers + tmem ptr*/ + EPI_BYTES;
-  static constexpr int STAGES_RAW = (kSmemLimit - AUX_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES;
+  static constexpr int EPI_WARP_BYTES_SIDE = 12288;
+  static_assert(EPI_ROW_SLOTS * EPI_SLOT_BYTES <= EPI_WARP_BYTES, "");
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int MAX_STAGES = 8;
+  static constexpr int stages_for(int epi_warp_bytes) {
+    const int n = (kSmemLimit - 1024 - BAR_BYTES - 4 * epi_warp_bytes) / STAGE_BYTES;
+    return n > MAX_STAGES ? MAX_STAGES : n;
+  }
+  static constexpr int smem_bytes(int stages, int epi_warp_bytes) {
+    return stages * STAGE_BYTES + 1024 + BAR_BYTES + 4 * epi_warp_bytes;
+  }
+  static_assert(stages_for(EPI_WARP_BYTES_SIDE) >= 3, "need a real pipeline");
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered fp32 accumulator
   static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
-  static_assert(STAGES >= 3, "need a real pipeline");
 };
 
 struct TileCoord {
@@ -149,7 +157,7 @@ __device__ __forceinline__ int rotate_group(int g, int rot, int mod) {
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ void unpack8(const uint4& u, bool is_bf16, float* f) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -175,11 +183,90 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, bool is_bf16) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// 32 floats -> 16 packed words; the dtype branch is taken ONCE per segment (a per-element branch on a kernel argument
+// serialises the unrolled loop and costs all its instruction-level parallelism).
+template <bool BF16>
+__device__ __forceinline__ void pack32_t(const float* v, uint32_t* w) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if constexpr (BF16) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    } else {
+      const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+  }
+}
+__device__ __forceinline__ void pack32(const float* v, uint32_t* w, bool is_bf16) {
+  if (is_bf16) pack32_t<true>(v, w); else pack32_t<false>(v, w);
+}
+template <bool BF16>
+__device__ __forceinline__ void unpack32_t(const uint4* p, float* f) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t w[4] = {p[q].x, p[q].y, p[q].z, p[q].w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if constexpr (BF16) {
+        f[q * 8 + 2 * i] = __uint_as_float(w[i] << 16);
+        f[q * 8 + 2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+      } else {
+        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        f[q * 8 + 2 * i] = t.x;
+        f[q * 8 + 2 * i + 1] = t.y;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void unpack32(const uint4* p, float* f, bool is_bf16) {
+  if (is_bf16) unpack32_t<true>(p, f); else unpack32_t<false>(p, f);
+}
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// GLU math on one 32-column segment, activation fixed at compile time (branch-free, fully interleavable).
+template <int ACT>
+__device__ __forceinline__ void glu_fwd_seg(const float* g, const float* u, float* o) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float a;
+    if constexpr (ACT == ACT_RELU) a = fmaxf(g[j], 0.0f);
+    else if constexpr (ACT == ACT_GELU) a = gelu_erf(g[j]);
+    else a = g[j] * fast_sigmoid(g[j]);
+    o[j] = a * u[j];
+  }
+}
+// in: dh (as raw accumulator bits), g, u      out: o = d gate, u = d up
+template <int ACT>
+__device__ __forceinline__ void glu_bwd_seg(const uint32_t* r, const float* g, float* u, float* o) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float dh = __uint_as_float(r[j]);
+    float a, da;
+    if constexpr (ACT == ACT_RELU) {
+      a = fmaxf(g[j], 0.0f);
+      da = g[j] > 0.0f ? 1.0f : 0.0f;
+    } else if constexpr (ACT == ACT_GELU) {
+      const float cdf = 0.5f * (1.0f + erff(g[j] * 0.70710678118654752f));
+      a = g[j] * cdf;
+      da = cdf + g[j] * 0.3989422804014327f * __expf(-0.5f * g[j] * g[j]);
+    } else {
+      const float sg = fast_sigmoid(g[j]);
+      a = g[j] * sg;
+      da = sg * (1.0f + g[j] * (1.0f - sg));
+    }
+    o[j] = dh * u[j] * da;
+    u[j] = dh * a;
+  }
+}
+
 template <int CG, bool A_MN, bool B_MN, int BN, int ELT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmD,
                   const __grid_constant__ CUtensorMap tmD2, const __grid_constant__ CUtensorMap tmD3,
+                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
                   const GemmArgs args) {
   using C = Cfg<CG, BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -191,15 +278,17 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   // ---- shared memory carve-up (operand ring must be 1024B aligned for the 128B swizzle) ----
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  const int stages = args.stages;
+  const uint32_t bar_base = smem_base + static_cast<uint32_t>(stages) * C::STAGE_BYTES;
   auto smem_a = [&](int s) { return smem_base + s * C::STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * C::STAGE_BYTES + C::A_BYTES; };
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
-  const uint32_t epi_base = bar_base + 512u;  // 16-byte aligned staging for the epilogue's row-wise bulk stores
+  auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
+  auto tfull_bar = [&](int a) { return bar_base + 128u + 8u * a; };
+  auto tempty_bar = [&](int a) { return bar_base + 144u + 8u * a; };
+  const uint32_t tmem_slot = bar_base + 160u;
+  auto side_bar = [&](int w, int st) { return bar_base + 192u + 8u * (w * 2 + st); };   // epilogue warp w, stage st
+  const uint32_t epi_base = bar_base + C::BAR_BYTES;  // 512-byte aligned staging of the epilogue warps
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
@@ -210,10 +299,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (args.tma_store) ptx::prefetch_tensormap(&tmD);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
+    for (int s = 0; s < stages; ++s) {
       ptx::mbar_init(full_bar(s), 1);
       ptx::mbar_init(empty_bar(s), 1);
     }
+    for (int w = 0; w < 8; ++w) ptx::mbar_init(side_bar(w >> 1, w & 1), 1);
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
       ptx::mbar_init(tempty_bar(a), 4 * CG);  // one arrival per epilogue warp of every CTA in the group
@@ -338,7 +428,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         __syncwarp();
-        if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+        if (++s == stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -386,7 +476,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (kb == num_kb - 1) ptx::umma_commit<CG>(tfull_bar(acc));  // accumulator complete
           }
           __syncwarp();
-          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+          if (++s == stages) { s = 0; ph ^= 1u; }
         }
         if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
       }
@@ -405,11 +495,54 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // accumulator);  (3) straight from registers (fp32, row_counts tails, TUTEL_B200_EPI=direct).
     const bool tma_out = out16 && args.tma_store != 0;
     const bool staged = out16 && args.staged_store != 0 && !tma_out && !glu;
-    const uint32_t epi_warp = epi_base + static_cast<uint32_t>(ew) * C::EPI_WARP_BYTES;
+    const uint32_t epi_warp = epi_base + static_cast<uint32_t>(ew) * static_cast<uint32_t>(args.epi_warp_bytes);
     int slot_toggle = 0;
+    // Side inputs (activation for the ReLU mask, pre-activations of the GLU backward, addend): lane 0 asks the TMA unit
+    // for the NEXT 32x32 segment (this tile's next columns, or the first segment of the next tile) while the warp works
+    // on the current one; the data lands in swizzled smem and is announced on a per-warp mbarrier, so no thread ever
+    // waits on a global load (there is only one epilogue warp per scheduler - nothing else could hide that latency).
+    const bool side = args.tma_side != 0;
+    const bool has_x2 = args.aux2 != nullptr;
+    const uint32_t side_base = epi_warp + 2u * C::EPI_TMA_SLOT_BYTES;
+    int side_stage = 0;
+    uint32_t side_phase = 0;
+    auto side_issue = [&](int st, int n, int m0, int g) {   // one lane
+      const uint32_t bar = side_bar(ew, st);
+      ptx::mbar_expect_tx(bar, has_x2 ? 2u * C::EPI_TMA_SLOT_BYTES : 1u * C::EPI_TMA_SLOT_BYTES);
+      ptx::tma_load_3d(side_base + static_cast<uint32_t>(st * 2) * C::EPI_TMA_SLOT_BYTES, &tmX, bar, n, m0, g);
+      if (has_x2) ptx::tma_load_3d(side_base + static_cast<uint32_t>(st * 2 + 1) * C::EPI_TMA_SLOT_BYTES, &tmX2, bar, n, m0, g);
+    };
+    auto side_coords = [&](long long t2, int& n0, int& m0, int& g) -> bool {
+      if (t2 >= args.num_tiles) return false;
+      TileCoord c2 = decode_tile<kBand>(t2, args.tiles_m, args.tiles_n);
+      g = rotate_group(c2.g, args.group_rot, args.group_mod);
+      n0 = c2.n_blk * tile_n;
+      m0 = c2.m_blk * C::BM + static_cast<int>(cta_rank) * C::BM_CTA + ew * 32;
+      return true;
+    };
+    if (side && lane == 0) {
+      int n0, m0, g;
+      if (side_coords(tile_first, n0, m0, g)) side_issue(0, n0, m0, g);
+    }
+    // The L2 is also asked for each thread's whole row segment of the NEXT tile one tile ahead, so DRAM sees long
+    // contiguous requests instead of 64-byte pieces.
+    auto prefetch_side = [&](long long t2) {
+      if (args.aux == nullptr || t2 >= args.num_tiles) return;
+      TileCoord c2 = decode_tile<kBand>(t2, args.tiles_m, args.tiles_n);
+      c2.g = rotate_group(c2.g, args.group_rot, args.group_mod);
+      const int m2 = c2.m_blk * C::BM + static_cast<int>(cta_rank) * C::BM_CTA + ew * 32 + lane;
+      const int n2 = c2.n_blk * tile_n;
+      if (m2 >= args.M || n2 >= args.N) return;
+      const uint32_t bytes = static_cast<uint32_t>(min(tile_n, args.N - n2)) * 2u;
+      const long long off = (static_cast<long long>(c2.g) * args.aux_group_stride + static_cast<long long>(m2) * args.ld_aux + n2) * 2;
+      ptx::prefetch_l2_bulk(reinterpret_cast<const uint8_t*>(args.aux) + off, bytes);
+      if (args.aux2 != nullptr) ptx::prefetch_l2_bulk(reinterpret_cast<const uint8_t*>(args.aux2) + off, bytes);
+    };
+    prefetch_side(tile_first);
     for (long long t = tile_first; t < args.num_tiles; t += tile_step) {
       TileCoord tc = decode_tile<kBand>(t, args.tiles_m, args.tiles_n);
       tc.g = rotate_group(tc.g, args.group_rot, args.group_mod);
+      prefetch_side(t + tile_step);
       int m_valid = args.M;
       if (args.row_counts != nullptr) {
         m_valid = min(args.M, args.row_counts[tc.g]);
@@ -440,21 +573,23 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // store per row segment, or direct 16-byte stores; fp32: direct).
       const int m_warp0 = tc.m_blk * C::BM + static_cast<int>(cta_rank) * C::BM_CTA + ew * 32;
       auto store_seg = [&](const CUtensorMap* tm, uint8_t* row, int n, int ncols, const float* v) {
+        uint32_t w[16];
+        if (out16) pack32(v, w, out_bf16);
         if (tma_out) {
           const uint32_t slot = epi_warp + static_cast<uint32_t>(slot_toggle) * C::EPI_TMA_SLOT_BYTES;
-          slot_toggle = (slot_toggle + 1) & (C::EPI_TMA_SLOTS - 1);
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");  // the store that used this slot has read it
+          slot_toggle = (slot_toggle + 1) & (side ? 1 : 3);        // 2 store slots next to side-input slots, else 4
+          if (lane == 0) {   // the store that used this slot has read it
+            if (side) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+          }
           __syncwarp();
           const uint32_t my = slot + static_cast<uint32_t>(lane) * 64u;
           const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;               // SWIZZLE_64B: 16-byte unit ^= row/2 % 4
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t o0 = pack2(v[q * 8 + 0], v[q * 8 + 1], out_bf16), o1 = pack2(v[q * 8 + 2], v[q * 8 + 3], out_bf16);
-            const uint32_t o2 = pack2(v[q * 8 + 4], v[q * 8 + 5], out_bf16), o3 = pack2(v[q * 8 + 6], v[q * 8 + 7], out_bf16);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(my + ((static_cast<uint32_t>(q) ^ sw) << 4)), "r"(o0),
-                         "r"(o1), "r"(o2), "r"(o3)
+          for (int q = 0; q < 4; ++q)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(my + ((static_cast<uint32_t>(q) ^ sw) << 4)),
+                         "r"(w[q * 4]), "r"(w[q * 4 + 1]), "r"(w[q * 4 + 2]), "r"(w[q * 4 + 3])
                          : "memory");
-          }
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -467,12 +602,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           slot_toggle = slot_toggle == C::EPI_ROW_SLOTS - 1 ? 0 : slot_toggle + 1;
           asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");  // the bulk store that used this slot has read it
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t o0 = pack2(v[q * 8 + 0], v[q * 8 + 1], out_bf16), o1 = pack2(v[q * 8 + 2], v[q * 8 + 3], out_bf16);
-            const uint32_t o2 = pack2(v[q * 8 + 4], v[q * 8 + 5], out_bf16), o3 = pack2(v[q * 8 + 6], v[q * 8 + 7], out_bf16);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + q * 16), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
+          for (int q = 0; q < 4; ++q)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot + q * 16), "r"(w[q * 4]), "r"(w[q * 4 + 1]),
+                         "r"(w[q * 4 + 2]), "r"(w[q * 4 + 3])
                          : "memory");
-          }
           ptx::fence_proxy_async_smem();
           if (row_ok)
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(row + n * 2), "r"(slot),
@@ -484,12 +617,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (q * 8 < ncols) {
-                uint4 o;
-                o.x = pack2(v[q * 8 + 0], v[q * 8 + 1], out_bf16);
-                o.y = pack2(v[q * 8 + 2], v[q * 8 + 3], out_bf16);
-                o.z = pack2(v[q * 8 + 4], v[q * 8 + 5], out_bf16);
-                o.w = pack2(v[q * 8 + 6], v[q * 8 + 7], out_bf16);
-                *reinterpret_cast<uint4*>(row + (n + q * 8) * 2) = o;
+                *reinterpret_cast<uint4*>(row + (n + q * 8) * 2) = make_uint4(w[q * 4], w[q * 4 + 1], w[q * 4 + 2], w[q * 4 + 3]);
               }
             }
           } else {
@@ -505,15 +633,50 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       };
       // 32 values of a 16-bit [.., ld] side input (zeros for rows past the end)
       auto load_seg16 = [&](const uint8_t* row, int n, int ncols, float* f) {
+        uint4 p[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (row_ok && q * 8 < ncols) {
-            unpack8(ptx::ld_nc_v4(row + (n + q * 8) * 2), out_bf16, f + q * 8);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[q * 8 + j] = 0.0f;
-          }
+        for (int q = 0; q < 4; ++q)
+          p[q] = (row_ok && q * 8 < ncols) ? ptx::ld_nc_v4(row + (n + q * 8) * 2) : make_uint4(0u, 0u, 0u, 0u);
+        unpack32(p, f, out_bf16);
+      };
+      const uint8_t* aux2_row = nullptr;
+      if (args.aux2 != nullptr)
+        aux2_row = reinterpret_cast<const uint8_t*>(args.aux2) +
+                   (static_cast<long long>(tc.g) * args.aux_group_stride + static_cast<long long>(m) * args.ld_aux) * 2;
+      const int nch = min(tile_n / 32, (args.N - tc.n_blk * tile_n + 31) / 32);   // 32-column segments of this tile
+      int nx_n = 0, nx_m = 0, nx_g = 0;
+      const bool nx_ok = side && side_coords(t + tile_step, nx_n, nx_m, nx_g);
+      // segment c of this tile: side inputs -> f0 (aux) and f1 (aux2, may be null)
+      auto side_fetch = [&](int c, int n, int ncols, float* f0, float* f1) {
+        if (!side) {
+          load_seg16(aux_row, n, ncols, f0);
+          if (f1 != nullptr) load_seg16(aux2_row, n, ncols, f1);
+          return;
         }
+        __syncwarp();   // every lane has finished reading the stage that is refilled next
+        if (lane == 0) {
+          if (c + 1 < nch) side_issue(side_stage ^ 1, n + 32, m_warp0, tc.g);
+          else if (nx_ok) side_issue(side_stage ^ 1, nx_n, nx_m, nx_g);
+        }
+        ptx::mbar_wait(side_bar(ew, side_stage), (side_phase >> side_stage) & 1u);
+        const uint32_t sw = (static_cast<uint32_t>(lane) >> 1) & 3u;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          float* f = a == 0 ? f0 : f1;
+          if (f == nullptr) continue;
+          const uint32_t my = side_base + static_cast<uint32_t>(side_stage * 2 + a) * C::EPI_TMA_SLOT_BYTES +
+                              static_cast<uint32_t>(lane) * 64u;
+          uint4 p[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(p[q].x), "=r"(p[q].y), "=r"(p[q].z), "=r"(p[q].w)
+                         : "r"(my + ((static_cast<uint32_t>(q) ^ sw) << 4))
+                         : "memory");
+          unpack32(p, f, out_bf16);
+        }
+        side_phase ^= 1u << side_stage;
+        side_stage ^= 1;
       };
 
       if (glu) {
@@ -522,31 +685,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const long long row_off = (static_cast<long long>(tc.g) * args.d_group_stride + static_cast<long long>(m) * args.ldd) * 2;
         uint8_t* d2_row = args.d2 != nullptr ? reinterpret_cast<uint8_t*>(args.d2) + row_off : nullptr;
         uint8_t* d3_row = args.d3 != nullptr ? reinterpret_cast<uint8_t*>(args.d3) + row_off : nullptr;
-        const uint8_t* aux2_row = nullptr;
-        if (args.aux2 != nullptr)
-          aux2_row = reinterpret_cast<const uint8_t*>(args.aux2) +
-                     (static_cast<long long>(tc.g) * args.aux_group_stride + static_cast<long long>(m) * args.ld_aux) * 2;
         const float sa = (args.scale_a != nullptr && row_ok)
                              ? args.scale_a[static_cast<long long>(tc.g) * args.scale_a_group_stride + m] : 1.0f;
-        // packed side inputs of the NEXT segment are fetched while the current one is computed (backward only)
-        uint4 pg[4], pu[4];
-        auto fetch_side = [&](int n, int ncols) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (row_ok && q * 8 < ncols) {
-              pg[q] = ptx::ld_nc_v4(aux_row + (n + q * 8) * 2);
-              pu[q] = ptx::ld_nc_v4(aux2_row + (n + q * 8) * 2);
-            } else {
-              pg[q] = make_uint4(0u, 0u, 0u, 0u);
-              pu[q] = make_uint4(0u, 0u, 0u, 0u);
-            }
-          }
-        };
-        if (!fwd && tc.n_blk * tile_n < args.N) fetch_side(tc.n_blk * tile_n, min(32, args.N - tc.n_blk * tile_n));
 #pragma unroll 1
-        for (int c = 0; c < tile_n / 32; ++c) {
+        for (int c = 0; c < nch; ++c) {
           const int n = tc.n_blk * tile_n + c * 32;
-          if (n >= args.N) break;  // warp-uniform
           const int ncols = min(32, args.N - n);
           uint32_t r[32];
           float g[32], u[32], o[32];
@@ -572,47 +715,23 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               store_seg(&tmD2, d2_row, n, ncols, g);
               store_seg(&tmD3, d3_row, n, ncols, u);
             }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float a = args.act == ACT_RELU ? fmaxf(g[j], 0.0f) : (args.act == ACT_GELU ? gelu_erf(g[j]) : silu(g[j]));
-              o[j] = a * u[j];
-            }
+            if (args.act == ACT_RELU) glu_fwd_seg<ACT_RELU>(g, u, o);
+            else if (args.act == ACT_GELU) glu_fwd_seg<ACT_GELU>(g, u, o);
+            else glu_fwd_seg<ACT_SILU>(g, u, o);
             store_seg(&tmD, d_row, n, ncols, o);
           } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              unpack8(pg[q], out_bf16, g + q * 8);
-              unpack8(pu[q], out_bf16, u + q * 8);
-            }
-            if (c + 1 < tile_n / 32 && n + 32 < args.N) fetch_side(n + 32, min(32, args.N - n - 32));
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float dh = __uint_as_float(r[j]);
-              float a, da;
-              if (args.act == ACT_RELU) {
-                a = fmaxf(g[j], 0.0f);
-                da = g[j] > 0.0f ? 1.0f : 0.0f;
-              } else if (args.act == ACT_GELU) {
-                const float cdf = 0.5f * (1.0f + erff(g[j] * 0.70710678118654752f));
-                a = g[j] * cdf;
-                da = cdf + g[j] * 0.3989422804014327f * __expf(-0.5f * g[j] * g[j]);
-              } else {
-                const float sg = 1.0f / (1.0f + __expf(-g[j]));
-                a = g[j] * sg;
-                da = sg * (1.0f + g[j] * (1.0f - sg));
-              }
-              o[j] = dh * u[j] * da;   // d gate
-              u[j] = dh * a;           // d up
-            }
+            side_fetch(c, n, ncols, g, u);
+            if (args.act == ACT_RELU) glu_bwd_seg<ACT_RELU>(r, g, u, o);
+            else if (args.act == ACT_GELU) glu_bwd_seg<ACT_GELU>(r, g, u, o);
+            else glu_bwd_seg<ACT_SILU>(r, g, u, o);
             store_seg(&tmD, d_row, n, ncols, o);
             store_seg(&tmD2, d2_row, n, ncols, u);
           }
         }
       } else {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < nch; ++c) {
         const int n = tc.n_blk * BN + c * 32;
-        if (n >= args.N) break;  // warp-uniform
         uint32_t r[32];
         ptx::tmem_ld_32x32(t_row + static_cast<uint32_t>(c * 32), r);
         ptx::tmem_ld_wait();
@@ -636,7 +755,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         } else if (args.epilogue == EPI_RELU_BWD || args.epilogue == EPI_ADD) {
           float f[32];
-          load_seg16(aux_row, n, ncols, f);
+          side_fetch(c, n, ncols, f, nullptr);
           if (args.epilogue == EPI_RELU_BWD) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = f[j] > 0.0f ? v[j] : 0.0f;
@@ -817,24 +936,27 @@ uint32_t make_idesc(int in_dtype, bool a_mn, bool b_mn, int umma_m, int umma_n) 
 }
 
 struct OutMaps {
-  CUtensorMap d, d2, d3;
+  CUtensorMap d, d2, d3, x, x2;   // outputs and side inputs (32x32 blocks, SWIZZLE_64B)
 };
 
 template <int CG, bool A_MN, bool B_MN, int BN, int ELT>
 cudaError_t launch_inst(const CUtensorMap& ta, const CUtensorMap& tb_, const CUtensorMap& tb2, const OutMaps& om,
-                        const GemmArgs& args, int grid, cudaStream_t stream) {
+                        const GemmArgs& args_in, int grid, cudaStream_t stream) {
   using C = Cfg<CG, BN>;
   auto* kern = gemm_sm100_kernel<CG, A_MN, B_MN, BN, ELT>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return e;
     configured = true;
   }
+  GemmArgs args = args_in;
+  args.epi_warp_bytes = args.tma_side ? C::EPI_WARP_BYTES_SIDE : C::EPI_WARP_BYTES;
+  args.stages = C::stages_for(args.epi_warp_bytes);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.dynamicSmemBytes = C::smem_bytes(args.stages, args.epi_warp_bytes);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -843,7 +965,7 @@ cudaError_t launch_inst(const CUtensorMap& ta, const CUtensorMap& tb_, const CUt
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, ta, tb_, tb2, om.d, om.d2, om.d3, args);
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb_, tb2, om.d, om.d2, om.d3, om.x, om.x2, args);
 }
 
 }  // namespace
@@ -928,8 +1050,9 @@ cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const c
 
   // Local 16-bit outputs leave through tensor stores (one per 32x32 block).
   OutMaps om;
-  om.d = ta; om.d2 = ta; om.d3 = ta;   // placeholders (never dereferenced unless tma_store is set)
+  om.d = ta; om.d2 = ta; om.d3 = ta; om.x = ta; om.x2 = ta;   // placeholders (dereferenced only when the flags are set)
   a.tma_store = 0;
+  a.tma_side = 0;
   if (a.staged_store && p.out_dtype != DT_FP32 && p.d_ptr_table == nullptr && p.row_counts == nullptr && p.d != nullptr) {
     if (!make_output_map(&om.d, p.d, p.out_dtype, p.M, p.N, p.ldd, p.d_group_stride, p.G, why)) return cudaErrorInvalidValue;
     if (p.d2 != nullptr && !make_output_map(&om.d2, p.d2, p.out_dtype, p.M, p.N, p.ldd, p.d_group_stride, p.G, why))
@@ -937,6 +1060,14 @@ cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const c
     if (p.d3 != nullptr && !make_output_map(&om.d3, p.d3, p.out_dtype, p.M, p.N, p.ldd, p.d_group_stride, p.G, why))
       return cudaErrorInvalidValue;
     a.tma_store = 1;
+    const bool uses_side = p.epilogue == EPI_RELU_BWD || p.epilogue == EPI_ADD || p.epilogue == EPI_GLU_BWD;
+    if (uses_side && p.aux != nullptr && ((reinterpret_cast<uintptr_t>(p.aux) | reinterpret_cast<uintptr_t>(p.aux2)) & 15) == 0 &&
+        ((p.ld_aux * 2) & 15) == 0 && ((p.aux_group_stride * 2) & 15) == 0) {
+      if (!make_output_map(&om.x, p.aux, p.out_dtype, p.M, p.N, p.ld_aux, p.aux_group_stride, p.G, why)) return cudaErrorInvalidValue;
+      if (p.aux2 != nullptr && !make_output_map(&om.x2, p.aux2, p.out_dtype, p.M, p.N, p.ld_aux, p.aux_group_stride, p.G, why))
+        return cudaErrorInvalidValue;
+      a.tma_side = 1;
+    }
   }
 
   long long want = a.num_tiles * cg;

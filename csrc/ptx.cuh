@@ -206,6 +206,11 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t smem_dst, const void* t
       : "memory");
 }
 
+// Ask the L2 to fetch `bytes` (multiple of 16) starting at a 16-byte aligned global address.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 // Tensor store smem -> global (bulk async group of the issuing thread); out-of-range rows / columns are clipped.
 __device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),

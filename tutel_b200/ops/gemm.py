@@ -245,14 +245,19 @@ def quantize_rows(x: torch.Tensor):
 def fp8_weight(w: torch.Tensor, layout: str):
     """K-major e4m3 copy [G, N, K] + per-output-channel scales [G, N] of a weight in 'nk' or 'kn' layout.
     Cached per (storage, version): weights are re-quantised only after they changed."""
-    key = (w.data_ptr(), layout, tuple(w.shape))
+    import weakref
+    anchor = w._base if w._base is not None else w      # views of a parameter are re-created every forward
+    key = (id(anchor), w.data_ptr(), layout, tuple(w.shape))
     ver = w._version
     hit = _FP8_WEIGHT_CACHE.get(key)
-    if hit is not None and hit[0] == ver:
+    if hit is not None and hit[0] == ver and hit[3]() is anchor:   # same live tensor, unchanged since quantisation
         return hit[1], hit[2]
     wk = w.detach() if layout == 'nk' else w.detach().transpose(1, 2)
     q, s = quantize_rows(wk.contiguous())
-    _FP8_WEIGHT_CACHE[key] = (ver, q, s)
+    if len(_FP8_WEIGHT_CACHE) > 256:
+        for k in [k for k, v in _FP8_WEIGHT_CACHE.items() if v[3]() is None]:
+            del _FP8_WEIGHT_CACHE[k]
+    _FP8_WEIGHT_CACHE[key] = (ver, q, s, weakref.ref(anchor))
     return q, s
 
 
@@ -286,8 +291,14 @@ def fused_relu_ffn_fp8(x, w1, b1, w2, b2, row_counts=None):
     return FusedReluFFNFp8.apply(x, w1, b1, w2, b2, row_counts)
 
 
+def _glu_extra(kw):
+    return (int(kw.get('b_group_div', 1)), int(kw.get('cta_group', 0)), int(kw.get('wait_flags', 0)),
+            int(kw.get('wait_rows_per_flag', 0)), int(kw.get('wait_flags_per_group', 0)), int(kw.get('wait_target', 0)),
+            int(kw.get('group_rot', 0)), int(kw.get('group_mod', 1)))
+
+
 def glu_gemm(a, b, b2, *, b_mn, act, save_pre=False, scale_a=None, scale_b=None, scale_b2=None, row_counts=None,
-             out_dtype=None):
+             out_dtype=None, **kw):
     """h = act(a @ B) * (a @ B2) in ONE tcgen05 launch (each CTA of a pair stages one of the two weight tiles; the
     gate/up halves meet in the TMEM accumulator).  ``save_pre`` also returns the pre-activations (g, u)."""
     C = backend.require_ext()
@@ -299,17 +310,17 @@ def glu_gemm(a, b, b2, *, b_mn, act, save_pre=False, scale_a=None, scale_b=None,
     h = torch.empty([a.size(0), a.size(1), N], dtype=dt, device=a.device)
     g, u = (torch.empty_like(h), torch.empty_like(h)) if save_pre else (None, None)
     backend.count_launch()
-    C.gemm_glu(a, b, b2, h, g, u, None, None, b_mn, ACT_CODES[act], scale_a, scale_b, scale_b2, row_counts)
+    C.gemm_glu(a, b, b2, h, g, u, None, None, b_mn, ACT_CODES[act], scale_a, scale_b, scale_b2, row_counts, *_glu_extra(kw))
     return h, g, u
 
 
-def glu_gemm_bwd(dy, w, g, u, *, b_mn, act, row_counts=None):
+def glu_gemm_bwd(dy, w, g, u, *, b_mn, act, row_counts=None, **kw):
     """(dg, du) for h = act(g) * u with dh = dy @ W formed in TMEM only (never written to memory)."""
     C = backend.require_ext()
     dy, w = _prep(dy), _prep(w)
     dg, du = torch.empty_like(g), torch.empty_like(g)
     backend.count_launch()
-    C.gemm_glu(dy, w, None, dg, du, None, g, u, b_mn, ACT_CODES[act], None, None, None, row_counts)
+    C.gemm_glu(dy, w, None, dg, du, None, g, u, b_mn, ACT_CODES[act], None, None, None, row_counts, *_glu_extra(kw))
     return dg, du
 
 

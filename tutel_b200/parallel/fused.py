@@ -77,7 +77,10 @@ class FusedEngine:
         self.t = transport
         self.W, self.rank = transport.world, transport.rank
         self.El, self.E = layer.num_local_experts, layer.num_global_experts
-        self.M, self.H, self.Mo = layer.model_dim, ex.hidden_size, ex.output_dim
+        if hasattr(ex, 'full_shapes'):       # llama_ffn: W_fc1/W_fc2 [El, M, H], W_fc3 [El, H, M]
+            self.M, self.H, self.Mo = layer.model_dim, int(ex.full_shapes['W_fc1'][2]), int(ex.full_shapes['W_fc3'][2])
+        else:
+            self.M, self.H, self.Mo = layer.model_dim, ex.hidden_size, ex.output_dim
         self.dtype, self.es = dtype, torch.empty((), dtype=dtype).element_size()
         FusedEngine._serial += 1                 # same creation order on every rank -> same names and offsets
         self.tag = 'moe%d' % FusedEngine._serial
@@ -152,11 +155,20 @@ def engine_for(layer, x: torch.Tensor, crit, d: int):
         return None
     ex = layer.experts
     from ..models.experts.ffn import FusedExpertsNetwork
-    if not isinstance(ex, FusedExpertsNetwork) or ex._act_kind != 'relu' or ex.skip_expert:
-        return None
+    from ..models.experts.llama_ffn import LlamaFFNNetwork
     if layer.sharded_count != 1 or layer.adaptive_degree != 1 or layer.megablocks_size > 0:
         return None
-    if ex.batched_fc1_w.dtype != x.dtype or (layer.model_dim % 8) or (ex.hidden_size % 8) or (ex.output_dim % 8):
+    if isinstance(ex, FusedExpertsNetwork):
+        if ex._act_kind != 'relu' or ex.skip_expert:
+            return None
+        if ex.batched_fc1_w.dtype != x.dtype or (layer.model_dim % 8) or (ex.hidden_size % 8) or (ex.output_dim % 8):
+            return None
+    elif isinstance(ex, LlamaFFNNetwork):
+        if ex.fp8 or G.classify_activation(ex.activation_fn) not in G.ACT_CODES or ex.W_fc1.dtype != x.dtype:
+            return None
+        if any(int(v) % 8 for v in ex.full_shapes['W_fc1'][1:]) or int(ex.full_shapes['W_fc3'][2]) != layer.model_dim:
+            return None
+    else:
         return None
     eng = layer.__dict__.get('_tb_fused_state', False)
     if eng is False:
@@ -189,6 +201,10 @@ class _Runner:
         eng, plan, bufs = self.eng, self.plan, self.bufs
         ex = layer.experts
         gates = crit.gates_ks if hasattr(crit, 'gates_ks') else torch.stack([g.view(-1) for g in crit[3]])
+        if hasattr(ex, 'full_shapes'):
+            w1, w2, w3 = (ex._full(n, layer.group) for n in ('W_fc1', 'W_fc2', 'W_fc3'))
+            return _FusedGLUMoE.apply(eng, bufs, plan, self.d, layer.is_postscore, G.classify_activation(ex.activation_fn),
+                                      x, gates, w1, w2, w3)
         return _FusedMoE.apply(eng, bufs, plan, self.d, layer.is_postscore, x, gates, ex.batched_fc1_w,
                                ex.batched_fc1_bias, ex.batched_fc2_w, ex.batched_fc2_bias)
 
@@ -321,3 +337,90 @@ class _FusedMoE(torch.autograd.Function):
         torch.cuda.current_stream().wait_event(ev)
         bufs.busy = False
         return None, None, None, None, None, dx, dgates, dw1, db1, dw2, db2
+
+
+class _FusedGLUMoE(torch.autograd.Function):
+    """The same engine for gated (SwiGLU / "LLaMA") experts: dispatch feeds the dual-B GLU GEMM tile by tile, the down
+    projection writes into the source GPUs' combine buffers; backward mirrors it with the fused GLU-gradient epilogue.
+    (reference: tutel/experts/llama_ffn.py:38-41 between the two all-to-alls of tutel/impls/moe_layer.py:349-351)"""
+
+    @staticmethod
+    def forward(ctx: Any, eng: FusedEngine, bufs: _BufferSet, plan: DispatchPlan, d: int, is_postscore: bool, act: str,
+                x, gates, w1, w2, w3):
+        t, W, El, E, rank = eng.t, eng.W, eng.El, eng.E, eng.rank
+        C, M, H, Mo = plan.C, eng.M, eng.H, eng.Mo
+        chunk = eng.chunk_rows(C, d)
+        bufs.epoch += 1
+        gates_f32 = gates.detach().to(torch.float32).contiguous()
+        base = t.base_ptr(rank)
+        need_grad = any(ctx.needs_input_grad[6:])
+        ev = _push(eng, bufs, plan, x, None if is_postscore else gates_f32, bufs.x_recv, bufs.f_disp, M, chunk)
+        x_recv = t.view(bufs.x_recv, [El * W, C, M], eng.dtype)
+        cg, _, _ = eng.tile_counts(C, H)
+        h, g, u = G.glu_gemm(x_recv, w1, w2, b_mn=True, act=act, save_pre=need_grad, b_group_div=W, cta_group=cg,
+                             wait_flags=base + bufs.f_disp, wait_rows_per_flag=chunk, wait_flags_per_group=_FLAGS_PER_SEG,
+                             wait_target=bufs.epoch, group_rot=rank, group_mod=-W)
+        cg2, bn2, tiles2 = eng.tile_counts(C, Mo)
+        d_tab, s_tab = eng.combine_tables(bufs, bufs.y_comb, bufs.f_comb, Mo)
+        y_comb = t.view(bufs.y_comb, [E, C, Mo], eng.dtype)
+        G.raw_gemm(h, w3, b_mn=True, b_group_div=W, out=y_comb, cta_group=cg2, block_n=bn2, d_ptr_table=d_tab,
+                   signal_ptr_table=s_tab, group_rot=rank, group_mod=-W)
+        bufs.comb_total[0] += tiles2
+        backend.count_launch()
+        out = backend.require_ext().decode_rows(y_comb.view(E * C, Mo), gates_f32 if is_postscore else None, plan.idx_ks,
+                                                plan.loc_ks, E, C, base + bufs.f_comb, bufs.comb_total[0])
+        torch.cuda.current_stream().wait_event(ev)
+        ctx.eng, ctx.bufs, ctx.plan, ctx.d, ctx.is_postscore, ctx.act = eng, bufs, plan, d, is_postscore, act
+        if need_grad:
+            ctx.save_for_backward(x, gates, w1, w2, w3, g, u, h)
+        return out
+
+    @staticmethod
+    def backward(ctx: Any, dout: torch.Tensor):
+        eng, bufs, plan, d, is_postscore, act = ctx.eng, ctx.bufs, ctx.plan, ctx.d, ctx.is_postscore, ctx.act
+        x, gates, w1, w2, w3, g, u, h = ctx.saved_tensors
+        t, W, El, E, rank = eng.t, eng.W, eng.El, eng.E, eng.rank
+        C, M, H, Mo = plan.C, eng.M, eng.H, eng.Mo
+        C_ext = backend.require_ext()
+        chunk = eng.chunk_rows(C, d)
+        base = t.base_ptr(rank)
+        dout = dout.contiguous()
+        gates_f32 = gates.detach().to(torch.float32).contiguous()
+        x_recv = t.view(bufs.x_recv, [El * W, C, M], eng.dtype)
+        y_comb = t.view(bufs.y_comb, [E * C, Mo], eng.dtype)
+        dgates = None
+        if is_postscore and ctx.needs_input_grad[7]:
+            backend.count_launch()
+            dgates = C_ext.gate_grad(dout, y_comb, plan.idx_ks, plan.loc_ks, E, C).to(gates.dtype)
+        bufs.epoch += 1
+        ev = _push(eng, bufs, plan, dout, gates_f32 if is_postscore else None, bufs.dy_recv, bufs.b_disp, Mo, chunk)
+        dy_recv = t.view(bufs.dy_recv, [El * W, C, Mo], eng.dtype)
+        cg, _, _ = eng.tile_counts(C, H)
+        # dh = dy @ W3^T stays in TMEM; the epilogue emits dg and du as the gradient rows arrive
+        dg, du = G.glu_gemm_bwd(dy_recv, w3, g, u, b_mn=False, act=act, b_group_div=W, cta_group=cg,
+                                wait_flags=base + bufs.b_disp, wait_rows_per_flag=chunk,
+                                wait_flags_per_group=_FLAGS_PER_SEG, wait_target=bufs.epoch, group_rot=rank, group_mod=-W)
+        need_dx = ctx.needs_input_grad[6] or (not is_postscore and ctx.needs_input_grad[7])
+        dx_comb = t.view(bufs.dx_comb, [E, C, M], eng.dtype)
+        if need_dx:
+            cgx, bnx, tilesx = eng.tile_counts(C, M)
+            d_tab, s_tab = eng.combine_tables(bufs, bufs.dx_comb, bufs.b_comb, M)
+            part = G.raw_gemm(dg, w1, b_group_div=W, cta_group=cgx, block_n=bnx)           # dg @ W1^T (local)
+            G.raw_gemm(du, w2, epilogue=G.EPI_ADD, aux=part, b_group_div=W, out=dx_comb, cta_group=cgx, block_n=bnx,
+                       d_ptr_table=d_tab, signal_ptr_table=s_tab, group_rot=rank, group_mod=-W)
+            bufs.comb_total[1] += tilesx
+        x_e, dy_e = x_recv.view(El, W * C, M), dy_recv.view(El, W * C, Mo)
+        dw3 = G.raw_gemm(h.view(El, W * C, H), dy_e, a_mn=True, b_mn=True) if ctx.needs_input_grad[10] else None
+        dw1 = G.raw_gemm(x_e, dg.view(El, W * C, H), a_mn=True, b_mn=True) if ctx.needs_input_grad[8] else None
+        dw2 = G.raw_gemm(x_e, du.view(El, W * C, H), a_mn=True, b_mn=True) if ctx.needs_input_grad[9] else None
+        dx = None
+        if need_dx:
+            backend.count_launch()
+            dx = C_ext.decode_rows(dx_comb.view(E * C, M), None if is_postscore else gates_f32, plan.idx_ks, plan.loc_ks,
+                                   E, C, base + bufs.b_comb, bufs.comb_total[1])
+        if not is_postscore and ctx.needs_input_grad[7]:
+            backend.count_launch()
+            dgates = C_ext.gate_grad(x, dx_comb.view(E * C, M), plan.idx_ks, plan.loc_ks, E, C).to(gates.dtype)
+        torch.cuda.current_stream().wait_event(ev)
+        bufs.busy = False
+        return None, None, None, None, None, None, dx, dgates, dw1, dw2, dw3
