@@ -49,7 +49,8 @@ def test_activation_classification():
     from tutel_b200.ops.gemm import classify_activation
     assert classify_activation(None) == 'relu' and classify_activation(F.relu) == 'relu'
     assert classify_activation(lambda x: F.relu(x)) == 'relu'
-    assert classify_activation(lambda x: F.gelu(x)) is None
+    assert classify_activation(lambda x: F.gelu(x)) == 'gelu' and classify_activation(F.silu) == 'silu'
+    assert classify_activation(lambda x: F.silu(x)) == 'silu' and classify_activation(torch.tanh) is None
     drop = torch.nn.Dropout(0.5)
     assert classify_activation(lambda x: drop(F.relu(x))) is None      # stochastic -> never fused
 
