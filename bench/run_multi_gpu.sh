@@ -20,9 +20,10 @@ except Exception as ex:
 timeout 300 $T --master-port 29599 tests/workers/p2p_worker.py all > $OUT/p2p_worker.log 2>&1; grep -cE "OK" $OUT/p2p_worker.log; grep -E "FAIL|timeout|WORKER_OK" $OUT/p2p_worker.log | head -5
 run bench_ours bench.py --gpus $N --steps 20 --warmup 5
 run bench_reference bench.py --impl reference --gpus $N --steps 20 --warmup 5
-TUTEL_B200_FUSED=0 run bench_ours_unfused bench.py --gpus $N --steps 20 --warmup 5
-if [ "$MODE" = "full" ]; then
-  run mixtral_ours_fp8_d2 bench.py --gpus $N --steps 10 --warmup 3 --expert_type llama_ffn --fp8 --overlap 2
+if [ "$MODE" != "lean" ]; then TUTEL_B200_FUSED=0 run bench_ours_unfused bench.py --gpus $N --steps 20 --warmup 5; fi
+if [ "$MODE" = "full" ] || [ "$MODE" = "lean" ]; then
+  run mixtral_ours_bf16_fused bench.py --gpus $N --steps 10 --warmup 3 --expert_type llama_ffn
+  TUTEL_B200_FUSED=0 run mixtral_ours_bf16_unfused_d2 bench.py --gpus $N --steps 10 --warmup 3 --expert_type llama_ffn --overlap 2
   run mixtral_reference_bf16_d2 bench.py --impl reference --gpus $N --steps 10 --warmup 3 --expert_type llama_ffn --overlap 2
   P=$((P+1)); timeout 300 $T --master-port $P -m tutel_b200.examples.bandwidth_test --sweep --compare_nccl --loop 10 --json $OUT/a2a_sweep.json > $OUT/a2a_sweep.log 2>&1
   grep -E "all_to_all" $OUT/a2a_sweep.log | tail -8

@@ -261,8 +261,12 @@ __device__ __forceinline__ void glu_bwd_seg(const uint32_t* r, const float* g, f
   }
 }
 
+// Resource budget (deliberate): 256 threads x 224 registers = 57344 of the SM's 65536 registers and at most 225.5 KB of
+// its 228 KB shared memory, so ONE 128-thread x 64-register block of the dispatch kernel (encode_rows, which needs no
+// shared memory) always fits next to a GEMM CTA.  That is what makes the dispatch+GEMM fusion deadlock-free: a GEMM
+// whose producer spins on arrival flags can never starve the kernel that publishes them, whichever gets the SMs first.
 template <int CG, bool A_MN, bool B_MN, int BN, int ELT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(224)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmD,
                   const __grid_constant__ CUtensorMap tmD2, const __grid_constant__ CUtensorMap tmD3,

@@ -193,11 +193,11 @@ __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return
 // ------------------------------------------------------------------------------------------------
 // encode: slot-centric row gather (+ optional remote push and release counters)
 // ------------------------------------------------------------------------------------------------
-constexpr int kEncThreads = 256;
-constexpr int kEncWarps = kEncThreads / 32;
+constexpr int kEncThreads = 256;      // local gather
+constexpr int kEncPushThreads = 128;  // remote push: 128 x 64 registers fit next to a resident GEMM CTA (gemm_sm100.cu)
 
-template <typename T, bool VEC>
-__global__ void __launch_bounds__(kEncThreads)
+template <typename T, bool VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS, 65536 / (THREADS * 64))
 encode_rows_kernel(const T* __restrict__ x, const float* __restrict__ gates, const int* __restrict__ slot_src,
                    T* __restrict__ out, const unsigned long long* __restrict__ dst_ptr_table,
                    const unsigned long long* __restrict__ signal_ptr_table, unsigned int* __restrict__ chunk_counters,
@@ -205,6 +205,7 @@ encode_rows_kernel(const T* __restrict__ x, const float* __restrict__ gates, con
                    uint32_t signal_value) {
   // Work unit = `unit_rows` consecutive slots of one expert (one warp per row).  Many blocks cooperate on one flag
   // chunk (`chunk_rows` rows); the block that finishes the chunk's last unit publishes the flag.
+  constexpr int kEncWarps = THREADS / 32;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int units_per_expert = (C + unit_rows - 1) / unit_rows;
@@ -575,16 +576,17 @@ static cudaError_t encode_rows_t(const void* x, const void* gates, const int* sl
   const int rot_units = rot_chunks * (chunk_rows / unit_rows);
   const bool vec = (M % Vec<T>::N == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                    (dst_ptr_table != nullptr || (reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  if (vec)
-    encode_rows_kernel<T, true><<<grid, kEncThreads, 0, stream>>>(
-        static_cast<const T*>(x), static_cast<const float*>(gates), slot_src, static_cast<T*>(out), dst_ptr_table,
-        signal_ptr_table, chunk_counters, chunk_rows, unit_rows, S, E, k, C, M, rot_units,
-        static_cast<uint32_t>(signal_value));
-  else
-    encode_rows_kernel<T, false><<<grid, kEncThreads, 0, stream>>>(
-        static_cast<const T*>(x), static_cast<const float*>(gates), slot_src, static_cast<T*>(out), dst_ptr_table,
-        signal_ptr_table, chunk_counters, chunk_rows, unit_rows, S, E, k, C, M, rot_units,
-        static_cast<uint32_t>(signal_value));
+#define TB_ENC_LAUNCH(VECv, THRv)                                                                                   \
+  encode_rows_kernel<T, VECv, THRv><<<grid, THRv, 0, stream>>>(                                                      \
+      static_cast<const T*>(x), static_cast<const float*>(gates), slot_src, static_cast<T*>(out), dst_ptr_table,     \
+      signal_ptr_table, chunk_counters, chunk_rows, unit_rows, S, E, k, C, M, rot_units,                             \
+      static_cast<uint32_t>(signal_value))
+  if (dst_ptr_table != nullptr) {
+    if (vec) TB_ENC_LAUNCH(true, kEncPushThreads); else TB_ENC_LAUNCH(false, kEncPushThreads);
+  } else {
+    if (vec) TB_ENC_LAUNCH(true, kEncThreads); else TB_ENC_LAUNCH(false, kEncThreads);
+  }
+#undef TB_ENC_LAUNCH
   return cudaGetLastError();
 }
 
