@@ -73,3 +73,48 @@ def test_launcher_builds_torchrun_command(monkeypatch):
     monkeypatch.setenv('LOCAL_RANK', '3')
     execl.main()
     assert seen['env']['CUDA_VISIBLE_DEVICES'] == '3' and seen['cmd'][-2:] == ['-m', 'my.prog']
+
+
+def test_fairseq_style_conversion(monkeypatch):
+    """examples/fairseq_moe: in-place conversion of fairseq-style transformer layers + aux-loss hook."""
+    from tutel_b200 import system
+    from tutel_b200.examples.fairseq_moe import add_moe_aux_loss, convert_transformer_layers, zero_overflow_grads
+
+    class Layer(torch.nn.Module):          # fairseq's TransformerDecoderLayerBase attribute layout
+        def __init__(self, d=16, h=32):
+            super().__init__()
+            self.embed_dim, self.quant_noise = d, 0
+            self.fc1, self.fc2 = torch.nn.Linear(d, h), torch.nn.Linear(h, d)
+            self.activation_fn = F.relu
+            self.activation_dropout_module = torch.nn.Dropout(0.0)
+            self.ffn_layernorm = torch.nn.LayerNorm(h)
+
+        def forward(self, x):
+            residual = x
+            x = self.activation_fn(self.fc1(x))
+            x = self.activation_dropout_module(x)
+            if self.ffn_layernorm is not None:
+                x = self.ffn_layernorm(x)
+            return residual + self.fc2(x)
+
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(*[Layer() for _ in range(4)])
+    monkeypatch.setenv('MOE', '2')
+    assert convert_transformer_layers(model) == 2
+    assert type(model[1].fc1).__name__ == 'MoEFeedForward' and isinstance(model[0].fc1, torch.nn.Linear)
+    assert all(getattr(p, 'expert', False) for n, p in model[1].fc1.moe_ffn.named_parameters() if 'experts' in n)
+    system.cache().reset()
+    x = torch.randn(3, 5, 16)
+    y = model(x)
+    assert y.shape == x.shape
+    records = system.cache().get()
+    assert len(records) == 2 and records[0][0] == 15
+    loss = add_moe_aux_loss(y.pow(2).mean(), l_aux_wt=0.01)
+    assert system.cache().get() == []
+    loss.backward()
+    assert model[1].fc1.moe_ffn.gates[0].wg.weight.grad is not None
+    assert model[1].fc1.ffn_layernorm.weight.grad is not None       # the moved layer-norm still trains
+    p = torch.nn.Parameter(torch.ones(3))
+    p.grad = torch.tensor([1.0, float('inf'), -float('inf')])
+    zero_overflow_grads([p], enabled=True)
+    assert p.grad.tolist() == [1.0, 0.0, 0.0]
