@@ -291,6 +291,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--case', type=int, default=-1)
     ap.add_argument('--filter', type=str, default='')
+    ap.add_argument('--no_perf', action='store_true', help='skip the large performance shapes (sanitizer runs)')
+    ap.add_argument('--inline', action='store_true', help='run the cases in this process (no subprocess per case)')
     ap.add_argument('--out', type=str, default=os.path.join(ROOT, 'gpurun_out', 'kernel_check.json'))
     args = ap.parse_args()
     if args.case >= 0:
@@ -306,7 +308,19 @@ def main():
     for i, c in enumerate(ALL):
         if args.filter and args.filter not in json.dumps(c):
             continue
+        if args.no_perf and (c.get('perf') or c.get('kind') == 'fp8'):
+            continue
         t0 = time.time()
+        if args.inline:
+            try:
+                r = RUNNERS[c['kind']](c)
+            except Exception as ex:  # noqa
+                r = dict(ok=False, error=repr(ex)[:500])
+            r['case'] = c
+            r['wall_s'] = round(time.time() - t0, 1)
+            results.append(r)
+            print(json.dumps(r), flush=True)
+            continue
         try:
             p = subprocess.run([sys.executable, os.path.abspath(__file__), '--case', str(i)], capture_output=True,
                                text=True, timeout=180)

@@ -30,3 +30,15 @@ def test_p2p_collectives_match_nccl():
 @pytest.mark.skipif(_ngpu() < 2, reason='needs 2 GPUs')
 def test_fused_engine_matches_nccl_path():
     _run('fused', 2)
+
+
+@pytest.mark.skipif(_ngpu() < 2 or os.environ.get('TUTEL_B200_TEST_FAULT', '0') != '1',
+                    reason='opt-in (TUTEL_B200_TEST_FAULT=1): kills its worker processes through a device trap after ~4 s')
+def test_dead_peer_is_diagnosed_not_hung():
+    """Fault injection: rank 1 skips one push collective; the other rank must report a peer-wait timeout and fail fast."""
+    env = dict(os.environ, TUTEL_B200_FAULT='skip_push:rank=1:call=2')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+           '--master-port', str(next_port()), os.path.join(ROOT, 'tests', 'workers', 'p2p_worker.py'), 'fault']
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert 'FIRST_OK' in p.stdout and p.returncode != 0
+    assert 'timeout' in p.stdout + p.stderr

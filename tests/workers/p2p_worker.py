@@ -120,6 +120,14 @@ def main():
         test_collectives(env)
     if which in ('all', 'fused'):
         test_fused_vs_nccl(env)
+    if which == 'fault':
+        # launched with TUTEL_B200_FAULT=skip_push:rank=1:call=2 - the second all-to-all must end in a diagnosed timeout
+        a = torch.ones(1 << 16, device=env.local_device)
+        net.simple_all_to_all(a)
+        torch.cuda.synchronize()
+        print('FIRST_OK', flush=True)
+        net.simple_all_to_all(a)
+        torch.cuda.synchronize()     # raises on the surviving ranks (device trap after the bounded spin)
     dist.barrier()
     if env.global_rank == 0:
         print('WORKER_OK', flush=True)

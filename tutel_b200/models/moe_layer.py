@@ -29,6 +29,7 @@ from ..ops.dispatch import fast_decode, fast_encode
 from ..ops.routing import extract_critical, get_dispatch_count
 from ..parallel import communicate as C
 from ..parallel.overlap import a2a_ffn_overlap_forward
+from ..utils.trace import stage
 from . import losses
 
 
@@ -288,11 +289,12 @@ class MOELayer(torch.nn.Module):
         if megablocks_size > 0 and (self.num_local_experts <= 1 or torch.is_grad_enabled() or self.world_size > 1):
             megablocks_size = 0
 
-        if x.is_cuda or x.device.type == 'cpu':
-            with torch.amp.autocast(x.device.type, enabled=False):
+        with stage('route'):
+            if x.is_cuda or x.device.type == 'cpu':
+                with torch.amp.autocast(x.device.type, enabled=False):
+                    logits_dtype, crit, l_aux = self._route(x, gctx, top_k, capacity_factor, d, megablocks_size, inequivalent_tokens)
+            else:
                 logits_dtype, crit, l_aux = self._route(x, gctx, top_k, capacity_factor, d, megablocks_size, inequivalent_tokens)
-        else:
-            logits_dtype, crit, l_aux = self._route(x, gctx, top_k, capacity_factor, d, megablocks_size, inequivalent_tokens)
 
         self.megablocks_size = megablocks_size
         self.dispatch_count = get_dispatch_count(crit)
@@ -303,12 +305,15 @@ class MOELayer(torch.nn.Module):
         y = None
         fused = self._fused_engine(x, crit, d, reserve_dims)
         if fused is not None:
-            y = fused.run(self, x, crit)
+            with stage('fused'):
+                y = fused.run(self, x, crit)
             self.protected_shape = y.shape
         else:
-            y = fast_encode(x, crit, self.is_postscore)
+            with stage('encode'):
+                y = fast_encode(x, crit, self.is_postscore)
             if self.adaptive_degree == 0:
-                y = self.expert_local(y, reserve_shape)
+                with stage('experts'):
+                    y = self.expert_local(y, reserve_shape)
             else:
                 sharded = self.num_global_experts < self.world_size
                 if sharded:
@@ -317,18 +322,23 @@ class MOELayer(torch.nn.Module):
                     else:
                         y = y.view(self.world_size, -1, y.size(2))
                 if d > 1 and y.is_cuda:
-                    y = a2a_ffn_overlap_forward(y, expert_fn=lambda t: self.expert_local(t, reserve_shape),
-                                                a2a_ffn_overlap_degree=d, use_2dh=self.use_2dh, group=self.group)
+                    with stage('overlap'):
+                        y = a2a_ffn_overlap_forward(y, expert_fn=lambda t: self.expert_local(t, reserve_shape),
+                                                    a2a_ffn_overlap_degree=d, use_2dh=self.use_2dh, group=self.group)
                 else:
-                    y = C.all_to_all(y, 1, 0, use_2dh=self.use_2dh, group=self.group)
-                    y = self.expert_local(y, reserve_shape)
-                    y = C.all_to_all(y, 0, 1, use_2dh=self.use_2dh, group=self.group)
+                    with stage('dispatch'):
+                        y = C.all_to_all(y, 1, 0, use_2dh=self.use_2dh, group=self.group)
+                    with stage('experts'):
+                        y = self.expert_local(y, reserve_shape)
+                    with stage('combine'):
+                        y = C.all_to_all(y, 0, 1, use_2dh=self.use_2dh, group=self.group)
                 if sharded:
                     if self.use_model_parallel:
                         y = torch.sum(y.view(self.num_global_experts, self.adaptive_degree, -1, y.size(2)), dim=1)
                     else:
                         y = y.view(self.num_global_experts, -1, y.size(2))
-            y = fast_decode(y.contiguous(), crit, self.is_postscore)
+            with stage('decode'):
+                y = fast_decode(y.contiguous(), crit, self.is_postscore)
 
         y = y.view(list(original_shape[:-reserve_dims]) + list(self.protected_shape[-reserve_dims:])).to(original_dtype)
         self.l_aux = y.l_aux = l_aux

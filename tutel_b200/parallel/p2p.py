@@ -106,8 +106,24 @@ class P2PTransport:
         # counter slots (512 B each): mailboxes uint64[16] at +0, done uint32[16] at +128, barrier at +192, local scratch
         # at +256
         self._epochs: Dict[int, int] = {}
+        self._fault = self._parse_fault(os.environ.get('TUTEL_B200_FAULT', ''))
+        self._fault_calls = 0
         self._named: Dict[str, tuple] = {}
         self._next_slot = 2  # slot 0: generic push, slot 1: generic barrier/reduce
+
+    # ---- fault injection (a dead peer must produce a diagnostic, not a hang) --------------------------
+    def _parse_fault(self, spec: str):
+        """``TUTEL_B200_FAULT=skip_push:rank=<r>:call=<n>``: rank r silently skips its n-th push collective (1-based)."""
+        if not spec.startswith('skip_push'):
+            return None
+        opts = dict(kv.split('=') for kv in spec.split(':')[1:] if '=' in kv)
+        if int(opts.get('rank', -1)) != self.rank:
+            return None
+        return int(opts.get('call', 1))
+
+    def _fault_fires(self) -> bool:
+        self._fault_calls += 1
+        return self._fault_calls == self._fault
 
     # ---- arena management -------------------------------------------------------------------------------------
     def alloc(self, name: str, nbytes: int, align: int = 1024) -> int:
@@ -179,6 +195,10 @@ class P2PTransport:
                    slot: int = 0) -> torch.Tensor:
         """Push-based collective with a zero-copy result: the receive buffer is taken from the arena pool, announced
         to the peers per call, and returned as a tensor (freed back to the pool when the tensor dies)."""
+        if self._fault is not None and self._fault_fires():
+            # fault injection (tests of the bounded-wait diagnostics): this rank "dies" for one collective - it neither
+            # announces a receive buffer nor pushes, so the peers' kernels hit their spin timeout and report it
+            return torch.zeros(list(out_shape), dtype=src.dtype, device=src.device)
         return self._C.p2p_collective(self.heap, src, src_off, dst_off, nbytes, list(out_shape), 512 * slot,
                                       self._next_epoch(slot), self._blocks_per_peer(max(nbytes)), self.stage_off,
                                       self.bounce_bytes)
