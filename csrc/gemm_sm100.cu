@@ -8,10 +8,12 @@
 //   warp 1      MMA issuer     one thread issues tcgen05.mma (kind::f16 / kind::f8f6f4), accumulators in TMEM,
 //                              tcgen05.commit releases smem slots / publishes the accumulator
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue       tcgen05.ld TMEM->registers, fused bias/activation/activation-grad, 16-byte
-//                              global stores - optionally straight into PEER GPUs' memory plus a release.sys
-//                              counter bump (GEMM -> combine all-to-all fusion), while the MMA warp already
-//                              works on the next tile in the second TMEM accumulator buffer.
+//   warps 4..7  epilogue       tcgen05.ld TMEM->registers, fused bias / activation / activation-grad / GLU / bias-grad
+//                              math, then swizzled smem and ONE TMA tensor store per 32x32 block (side inputs arrive
+//                              the same way, by tensor loads one segment ahead) - or per-row bulk stores straight
+//                              into PEER GPUs' memory plus a release.sys counter bump (GEMM -> combine all-to-all
+//                              fusion) - while the MMA warp already works on the next tile in the second TMEM
+//                              accumulator buffer.
 //
 // The producer can also acquire system-scope "rows have arrived" counters before loading an A tile, which is
 // how the dispatch all-to-all is overlapped tile-by-tile with the first expert GEMM.
@@ -116,6 +118,8 @@ struct Cfg {
     return stages * STAGE_BYTES + 1024 + BAR_BYTES + 4 * epi_warp_bytes;
   }
   static_assert(stages_for(EPI_WARP_BYTES_SIDE) >= 3, "need a real pipeline");
+  // 228 KB per SM, 1 KB reserved per resident block: a dispatch block (no shared memory of its own) must still fit
+  static_assert(smem_bytes(stages_for(EPI_WARP_BYTES), EPI_WARP_BYTES) + 2 * 1024 <= 228 * 1024, "no room for the push kernel");
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered fp32 accumulator
   static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
 };
@@ -174,15 +178,6 @@ __device__ __forceinline__ void unpack8(const uint4& u, bool is_bf16, float* f) 
     }
   }
 }
-__device__ __forceinline__ uint32_t pack2(float a, float b, bool is_bf16) {
-  if (is_bf16) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&h);
-  }
-  const __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-
 // 32 floats -> 16 packed words; the dtype branch is taken ONCE per segment (a per-element branch on a kernel argument
 // serialises the unrolled loop and costs all its instruction-level parallelism).
 template <bool BF16>
