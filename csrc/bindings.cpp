@@ -231,6 +231,33 @@ std::vector<at::Tensor> gate_topk_forward(const at::Tensor& logits, int64_t k) {
   return {scores, idx, top, me, ce};
 }
 
+at::Tensor gate_topk_backward(const at::Tensor& scores, const at::Tensor& idx, const at::Tensor& top,
+                              const at::Tensor& dgates, const c10::optional<at::Tensor>& ce,
+                              const c10::optional<at::Tensor>& dl, bool normalize, double eps) {
+  TORCH_CHECK(scores.is_cuda() && scores.scalar_type() == at::kFloat && scores.dim() == 2 && scores.is_contiguous());
+  const int S = static_cast<int>(scores.size(0)), E = static_cast<int>(scores.size(1));
+  const int k = static_cast<int>(idx.size(0));
+  TORCH_CHECK(idx.scalar_type() == at::kInt && idx.is_contiguous() && idx.size(1) == S);
+  TORCH_CHECK(top.scalar_type() == at::kFloat && top.is_contiguous() && top.sizes() == idx.sizes());
+  TORCH_CHECK(dgates.scalar_type() == at::kFloat && dgates.is_contiguous() && dgates.sizes() == idx.sizes());
+  const float* ce_p = nullptr;
+  const float* dl_p = nullptr;
+  if (ce.has_value() && ce->defined()) {
+    TORCH_CHECK(ce->is_cuda() && ce->scalar_type() == at::kFloat && ce->is_contiguous() && ce->numel() == E);
+    ce_p = ce->data_ptr<float>();
+  }
+  if (dl.has_value() && dl->defined()) {
+    TORCH_CHECK(dl->is_cuda() && dl->scalar_type() == at::kFloat && dl->numel() == 1);
+    dl_p = dl->data_ptr<float>();
+  }
+  const c10::cuda::CUDAGuard guard(scores.device());
+  at::Tensor out = at::empty_like(scores);
+  TB_CHECK_CUDA(tb::gate_topk_backward(scores.data_ptr<float>(), idx.data_ptr<int>(), top.data_ptr<float>(),
+                                       dgates.data_ptr<float>(), ce_p, dl_p, out.data_ptr<float>(), S, E, k, normalize,
+                                       static_cast<float>(eps), cur_stream()));
+  return out;
+}
+
 std::vector<at::Tensor> quantize_rows(const at::Tensor& x) {
   TORCH_CHECK(x.is_cuda() && x.is_contiguous() && x.dim() >= 2, "quantize_rows: contiguous CUDA tensor [.., K] expected");
   const c10::cuda::CUDAGuard guard(x.device());
@@ -363,6 +390,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("decode_rows", &decode_rows);
   m.def("gate_grad", &gate_grad);
   m.def("gate_topk_forward", &gate_topk_forward);
+  m.def("gate_topk_backward", &gate_topk_backward);
   m.def("skinny_gemm", &skinny_gemm);
   m.def("quantize_rows", &quantize_rows);
   register_symm_bindings(m);

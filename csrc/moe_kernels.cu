@@ -481,6 +481,63 @@ gate_topk_kernel(const float* __restrict__ logits, float* __restrict__ scores, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// fused gating backward: d logits from the gradients of the (normalised) top-k gates and of the GShard auxiliary
+// loss, one warp per token:
+//   r_j  = p[idx_j]                       raw top-k scores,      D = sum_j r_j,  Dc = max(D, eps)
+//   g_j  = r_j / Dc   (normalize && k>1)  ->  dr_j = dg_j / Dc - [D > eps] * (sum_i dg_i r_i) / Dc^2
+//   dp_e = dl * ce_e * E / S^2 + sum_j [idx_j == e] dr_j          (l_aux = E / S^2 * sum_e me_e * ce_e, ce constant)
+//   dlogit_e = p_e * (dp_e - sum_e' dp_e' p_e')                   (softmax)
+// ------------------------------------------------------------------------------------------------
+template <int VPT>
+__global__ void __launch_bounds__(256)
+gate_topk_bwd_kernel(const float* __restrict__ scores, const int* __restrict__ idx, const float* __restrict__ topk_scores,
+                     const float* __restrict__ dgates, const float* __restrict__ ce, const float* __restrict__ dl,
+                     float* __restrict__ dlogits, int S, int E, int k, int normalize, float eps) {
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const float aux_scale = (dl != nullptr ? dl[0] : 0.0f) * static_cast<float>(E) /
+                          (static_cast<float>(S) * static_cast<float>(S));
+  for (long long s = static_cast<long long>(blockIdx.x) * 8 + warp; s < S; s += static_cast<long long>(gridDim.x) * 8) {
+    float p[VPT], dp[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int e = lane + 32 * i;
+      p[i] = e < E ? scores[s * E + e] : 0.0f;
+      dp[i] = (e < E && ce != nullptr) ? aux_scale * ce[e] : 0.0f;
+    }
+    // every lane reads the k (<= 32) choices of this token redundantly: tiny and L1-resident
+    float D = 0.0f, dot = 0.0f;
+    for (int j = 0; j < k; ++j) {
+      const float r = topk_scores[static_cast<long long>(j) * S + s];
+      D += r;
+      dot += dgates[static_cast<long long>(j) * S + s] * r;
+    }
+    const bool norm = normalize != 0 && k > 1;
+    const float Dc = fmaxf(D, eps);
+    for (int j = 0; j < k; ++j) {
+      const int e = idx[static_cast<long long>(j) * S + s];
+      float dr = dgates[static_cast<long long>(j) * S + s];
+      if (norm) dr = dr / Dc - (D > eps ? dot / (Dc * Dc) : 0.0f);
+      if (e >= 0 && (e & 31) == lane) {
+#pragma unroll
+        for (int i = 0; i < VPT; ++i)
+          if (i == (e >> 5)) dp[i] += dr;
+      }
+    }
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) acc += dp[i] * p[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int e = lane + 32 * i;
+      if (e < E) dlogits[s * E + e] = p[i] * (dp[i] - acc);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-row e4m3 quantisation (activations / K-major weights for the fp8 tcgen05 GEMM): one warp per row
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -700,6 +757,25 @@ cudaError_t gate_topk_forward(const float* logits, float* scores, int* idx, floa
   else if (E <= 512) TB_GATE(16);
   else return cudaErrorInvalidValue;
 #undef TB_GATE
+  return cudaGetLastError();
+}
+
+cudaError_t gate_topk_backward(const float* scores, const int* idx, const float* topk_scores, const float* dgates,
+                               const float* ce, const float* dl, float* dlogits, int S, int E, int k, bool normalize,
+                               float eps, cudaStream_t stream) {
+  if (S <= 0) return cudaSuccess;
+  const long long want_blocks = (static_cast<long long>(S) + 7) / 8;
+  const int grid = static_cast<int>(want_blocks < 4LL * num_sms() ? want_blocks : 4LL * num_sms());
+#define TB_GATE_BWD(VPTv)                                                                                          \
+  gate_topk_bwd_kernel<VPTv><<<grid, 256, 0, stream>>>(scores, idx, topk_scores, dgates, ce, dl, dlogits, S, E, k,   \
+                                                       normalize ? 1 : 0, eps)
+  if (E <= 32) TB_GATE_BWD(1);
+  else if (E <= 64) TB_GATE_BWD(2);
+  else if (E <= 128) TB_GATE_BWD(4);
+  else if (E <= 256) TB_GATE_BWD(8);
+  else if (E <= 512) TB_GATE_BWD(16);
+  else return cudaErrorInvalidValue;
+#undef TB_GATE_BWD
   return cudaGetLastError();
 }
 

@@ -48,6 +48,12 @@ cudaError_t gate_grad(const void* a, const void* buf, const int* idx, const int*
 cudaError_t gate_topk_forward(const float* logits, float* scores, int* idx, float* topk_scores, float* me_partial,
                               int* ce_partial, int S, int E, int k, cudaStream_t stream);
 
+// Fused gating backward (see the kernel for the formulas): gradients of the normalised top-k gates [k,S] and of the
+// GShard loss (device scalar `dl`, may be null) -> d logits [S,E].  `ce` = first-choice counts per expert (fp32 [E]).
+cudaError_t gate_topk_backward(const float* scores, const int* idx, const float* topk_scores, const float* dgates,
+                               const float* ce, const float* dl, float* dlogits, int S, int E, int k, bool normalize,
+                               float eps, cudaStream_t stream);
+
 // q[r, :] = e4m3(x[r, :] / scale[r]),  scale[r] = max|x[r, :]| / 448   (one scale per row; rows are K-major GEMM
 // operands, so the scale factors out of the dot product and is applied in the GEMM epilogue).
 cudaError_t quantize_rows_e4m3(const void* x, void* q, float* scale, long long R, int K, int elem_type,

@@ -324,3 +324,24 @@ def test_llama_ffn_expert_fused_glu_matches_autograd(act, fp8):
         assert errs[0] < 0.1 and max(errs) < 0.3, errs
     else:       # bf16: rounding of the saved activations
         assert max(errs) < 0.02, errs
+
+
+@pytest.mark.skipif(__import__('os').environ.get('TUTEL_B200_TEST_EXPERIMENTAL', '0') != '1',
+                    reason='opt-in: fused gating path (TUTEL_B200_FUSED_GATE) is not enabled by default yet')
+@pytest.mark.parametrize('E,k', [(8, 2), (130, 4)])
+def test_fused_gate_autograd_cuda_matches_torch_branch(E, k):
+    """CUDA gate_topk_forward/backward kernels vs the pure-torch branch of ops/gating.FusedTopKGate (CPU-verified)."""
+    from tutel_b200.ops.gating import fused_topk_gate
+    torch.manual_seed(6)
+    S = 777
+    base = torch.randn(S, E)
+    wg = torch.randn(k, S)
+    outs = []
+    for dev in ('cpu', 'cuda'):
+        logits = base.to(dev).requires_grad_(True)
+        idx, gates, l_aux, top1 = fused_topk_gate(logits, k, True, True)
+        ((gates * wg.to(dev)).sum() + 2.0 * l_aux).backward()
+        outs.append((idx.cpu(), gates.detach().cpu(), l_aux.detach().cpu(), logits.grad.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert torch.allclose(a, b, atol=2e-6, rtol=1e-4)

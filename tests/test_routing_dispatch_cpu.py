@@ -144,3 +144,49 @@ def test_fast_cumsum_sub_one():
     assert torch.equal(moe.fast_cumsum_sub_one(m), torch.cumsum(m, 0) - 1)
     with pytest.raises(Exception):
         moe.fast_cumsum_sub_one(m, dim=1)
+
+
+@pytest.mark.parametrize('k,normalize', [(1, True), (2, True), (2, False), (4, True)])
+def test_fused_topk_gate_formulas_match_autograd(k, normalize):
+    """ops/gating.FusedTopKGate (closed-form backward, same math as the CUDA kernels) vs autograd of the unfused ops."""
+    from tutel_b200.models import losses
+    from tutel_b200.ops.gating import fused_topk_gate
+    torch.manual_seed(0)
+    S, E = 37, 10
+    logits = torch.randn(S, E, requires_grad=True)
+    wg = torch.randn(k, S)
+    # reference: separate softmax / topk / normalisation / loss, differentiated by autograd
+    p = torch.softmax(logits, dim=1)
+    ti = torch.topk(p, k, dim=1).indices
+    g = p.gather(1, ti).t()
+    if normalize and k > 1:
+        g = g / torch.clamp(g.sum(dim=0, keepdim=True), min=torch.finfo(g.dtype).eps)
+    l_ref = losses.gshard_loss(p, ti)
+    ((g * wg).sum() + 3.0 * l_ref).backward()
+    ref_grad = logits.grad.clone()
+    logits.grad = None
+    idx, gates, l_aux, top1 = fused_topk_gate(logits, k, normalize, True)
+    assert torch.equal(idx.long(), ti.t()) and torch.allclose(gates, g.detach(), atol=1e-6)
+    assert torch.allclose(l_aux, l_ref.detach(), atol=1e-6) and torch.allclose(top1, p.max(dim=1)[0].detach(), atol=1e-6)
+    ((gates * wg).sum() + 3.0 * l_aux).backward()
+    assert torch.allclose(logits.grad, ref_grad, atol=2e-6, rtol=1e-4)
+
+
+def test_layer_with_fused_gate_matches_default_path(monkeypatch):
+    from tutel_b200 import moe
+
+    def run(fused, bpr):
+        monkeypatch.setenv('TUTEL_B200_FUSED_GATE', '1' if fused else '0')
+        torch.manual_seed(3)
+        layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2, 'capacity_factor': 1.5}, model_dim=16,
+                              experts={'type': 'ffn', 'num_experts_per_device': 4, 'hidden_size_per_expert': 32},
+                              batch_prioritized_routing=bpr)
+        x = torch.randn(48, 16, requires_grad=True)
+        y = layer(x)
+        (y.pow(2).mean() + 0.1 * y.l_aux).backward()
+        return y.detach(), y.l_aux.detach(), x.grad.clone(), layer.gates[0].wg.weight.grad.clone()
+
+    for bpr in (False, True):
+        a, b = run(True, bpr), run(False, bpr)
+        for u, v in zip(a, b):
+            assert torch.allclose(u, v, atol=1e-5, rtol=1e-4)

@@ -26,6 +26,7 @@ from torch import Tensor
 from torch.nn import ModuleList
 
 from ..ops.dispatch import fast_decode, fast_encode
+from ..ops.gating import fused_gate_enabled, fused_topk_gate
 from ..ops.routing import extract_critical, get_dispatch_count
 from ..parallel import communicate as C
 from ..parallel.overlap import a2a_ffn_overlap_forward
@@ -244,7 +245,14 @@ class MOELayer(torch.nn.Module):
             logits_w_noise = logits + gctx.gate_noise * torch.randn_like(logits) / self.num_global_experts
         else:
             logits_w_noise = logits
-        scores = F.softmax(logits_w_noise, dim=1)
+        fused_gate = None
+        if self.is_gshard_loss and fused_gate_enabled() and logits_w_noise.dim() == 2:
+            # one kernel forward / one backward for softmax + top-k + gate normalisation + GShard loss (ops/gating.py)
+            k_eff = min(top_k, self.num_global_experts)
+            fused_gate = fused_topk_gate(logits_w_noise, k_eff, self.normalize_gate, True)
+            scores = logits_w_noise                # only its shape is read below
+        else:
+            scores = F.softmax(logits_w_noise, dim=1)
         if self.is_gshard_loss:
             loss_fn = losses.gshard_loss
         else:
@@ -259,7 +267,7 @@ class MOELayer(torch.nn.Module):
                                        capacity_factor=capacity_factor or gctx.capacity_factor,
                                        batch_prioritized_routing=self.batch_prioritized_routing,
                                        normalize_gate=self.normalize_gate, group=self.group, alignment=alignment,
-                                       inequivalent_tokens=inequivalent_tokens)
+                                       inequivalent_tokens=inequivalent_tokens, _fused=fused_gate)
         return logits.dtype, crit, l_aux
 
     def forward(self, input: Tensor, gate_index=0, capacity_factor=None, top_k=None, a2a_ffn_overlap_degree=None,

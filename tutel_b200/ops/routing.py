@@ -75,25 +75,32 @@ def build_slot_map(idx_ks: torch.Tensor, loc_ks: torch.Tensor, E: int, C: int) -
 
 def extract_critical(scores: torch.Tensor, top_k: int, loss_fn=losses.gshard_loss, capacity_factor: float = 1.0,
                      batch_prioritized_routing: bool = False, normalize_gate: bool = True, alignment: int = 1,
-                     group=None, inequivalent_tokens: bool = False):
+                     group=None, inequivalent_tokens: bool = False, _fused=None):
+    """``_fused`` (internal): ``(idx_ks, gates_ks, l_aux, top1)`` from :func:`tutel_b200.ops.gating.fused_topk_gate` -
+    top-k selection, gate normalisation and the auxiliary loss were then already computed by the fused kernel."""
     num_global_experts = int(scores.size(1))
     top_k_original, top_k = top_k, min(top_k, num_global_experts)
-    topk_indices = torch.topk(scores, top_k, dim=1).indices                     # [S, k]
-    idx_ks = topk_indices.t().contiguous().to(torch.int32)                      # [k, S]
-    gates_ks = scores.gather(1, topk_indices).t()                               # [k, S], differentiable
-
-    l_loss = loss_fn(scores, topk_indices) if loss_fn is not None else None
+    if _fused is None:
+        topk_indices = torch.topk(scores, top_k, dim=1).indices                     # [S, k]
+        idx_ks = topk_indices.t().contiguous().to(torch.int32)                      # [k, S]
+        gates_ks = scores.gather(1, topk_indices).t()                               # [k, S], differentiable
+        l_loss = loss_fn(scores, topk_indices) if loss_fn is not None else None
+        confidence = None
+    else:
+        idx_ks, gates_ks, l_loss, confidence = _fused
 
     if batch_prioritized_routing:
         # tokens claim slots in order of decreasing confidence instead of batch order
-        order = (-scores.max(dim=1)[0]).argsort(dim=0)
+        if confidence is None:
+            confidence = scores.max(dim=1)[0]
+        order = (-confidence).argsort(dim=0)
         loc_sorted, counts = _locations(idx_ks[:, order].contiguous(), num_global_experts)
         loc_ks = torch.empty_like(loc_sorted)
         loc_ks[:, order] = loc_sorted
     else:
         loc_ks, counts = _locations(idx_ks, num_global_experts)
 
-    if top_k > 1 and normalize_gate:
+    if _fused is None and top_k > 1 and normalize_gate:
         denom = torch.clamp(gates_ks.sum(dim=0, keepdim=True), min=torch.finfo(gates_ks.dtype).eps)
         gates_ks = gates_ks / denom
 
