@@ -34,6 +34,13 @@ cfg = y.autotune(total_nodes=1, spmd_nodes=1, device_type='cpu', config_file=sys
 assert os.path.exists(sys.argv[1]) and cfg.config['v'] == '0.1' and y.name in cfg.config['b']
 res = y.compile(cfg).execute()
 assert res.get('step_time', 0) > 0, res
+# the generated 2-way tensor-parallel and 2-way data-parallel programs really run (2 Gloo ranks) and compute the same
+# first output element as the single-process program
+res_tp = y.compile(tp, total_nodes=2, spmd_nodes=2, device_type='cpu', run_mode='train').execute()
+res_dp = y.compile(dp).execute()
+assert res_tp.get('step_time', 0) > 0 and res_dp.get('step_time', 0) > 0, (res_tp, res_dp)
+assert abs(res_tp['digest'] - res['digest']) <= 1e-6 * max(1.0, abs(res['digest'])), (res_tp, res)
+assert abs(res_dp['digest'] - res['digest']) <= 1e-6 * max(1.0, abs(res['digest'])), (res_dp, res)
 # sharded code generation (not executed): 2-way tensor parallel hidden dim
 cfg2 = {n: v for n, v in cfg.config['b'].items()}
 print('PARTED_OK', json.dumps(cfg.config['b']))

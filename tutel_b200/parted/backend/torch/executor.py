@@ -101,7 +101,7 @@ def model_executor(module, is_training=True):
     if parallel_env.global_rank == 0:
         if verbose:
             sys.stderr.write('  [%s] digest = %g .., time = %g\n' % (name, digest, step_time))
-        result = json.dumps({'name': name, 'step_time': step_time})
+        result = json.dumps({'name': name, 'step_time': step_time, 'digest': digest})
         if 'CONFIG_STORE_PATH' in os.environ:
             with open(os.environ['CONFIG_STORE_PATH'], 'w') as f:
                 f.write(result)

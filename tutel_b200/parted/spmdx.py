@@ -134,6 +134,9 @@ class Config:
         return json.dumps(self.config)
 
 
+_UNSET = object()
+
+
 def environ_config(kwargs):
     kwargs.setdefault('spmd_nodes', kwargs['total_nodes'])
     kwargs.setdefault('device_type', os.environ.get('DEVICE', 'cuda'))
@@ -200,6 +203,14 @@ class Custom:
     def _link_consumers(self, parent, kwargs):
         if parent is not None and parent not in self.outputs:
             self.outputs.append(parent)
+        # States pinned by an earlier serialisation (e.g. one with spmd_nodes == 1) must not leak into the next one:
+        # remember what the user pinned (strict format / node.config = ...) the first time and start from that.
+        if '_user_config' not in self.__dict__:
+            self._user_config = self.__dict__.get('config', _UNSET)
+        if self._user_config is _UNSET:
+            self.__dict__.pop('config', None)
+        else:
+            self.config = self._user_config
         if kwargs['spmd_nodes'] == 1:
             self.config = -1
         elif session.ptype == 'dp':
