@@ -139,3 +139,33 @@ else:
     scatter.main(['--input', str(tmp_path / 'full.ckpt'), '--output_size', '2', '--outputs', str(tmp_path / '{rank}-of-{size}.ckpt')])
     out = run_workers(body, nproc=2, env=env)
     assert 'RESHARD_OK' in out
+
+
+WORKER_2DH = r'''
+sys.path.insert(0, os.getcwd())
+from tutel_b200 import net, system
+env = system.init_data_model_parallel(backend='gloo')
+W, r = env.global_size, env.global_rank
+os.environ['LOCAL_SIZE'] = '2'                      # 4 ranks = 2 "nodes" x 2 "GPUs": the real two-phase path
+torch.manual_seed(100 + r)
+x = torch.randn(W * 3, 5, 7, dtype=torch.float64, requires_grad=True)
+flat = net.all_to_all(x, 1, 0)
+hier = net.all_to_all(x, 1, 0, use_2dh=True)
+assert torch.equal(flat, hier), (flat - hier).abs().max()
+w = torch.randn_like(hier)
+(hier * w).sum().backward()
+g_hier = x.grad.clone(); x.grad = None
+(net.all_to_all(x, 1, 0) * w).sum().backward()
+assert torch.equal(g_hier, x.grad)
+back = net.all_to_all(hier.detach(), 0, 1, use_2dh=True)
+assert torch.equal(back, x.detach())
+net.barrier()
+if r == 0:
+    print('HIER_OK')
+'''
+
+
+def test_two_phase_2dh_all_to_all_equals_flat_on_2x2_ranks():
+    """The hierarchical (intra-node then inter-node) exchange - untested in the reference for nnodes > 1 (SURVEY §4)."""
+    out = run_workers(WORKER_2DH, nproc=4)
+    assert 'HIER_OK' in out
