@@ -19,6 +19,10 @@ def test_overlap_degree_does_not_change_results(nle):
     a = run_helloworld(nproc=2, extra=base + ['--a2a_ffn_overlap_degree', 1])
     b = run_helloworld(nproc=2, extra=base + ['--a2a_ffn_overlap_degree', 2])
     assert a == b
+    # the same through the chunked pipeline of parallel/overlap.py (async exchanges + autograd Functions), which the
+    # layer only selects on CUDA unless this testing hook is set
+    c = run_helloworld(nproc=2, extra=base + ['--a2a_ffn_overlap_degree', 2], env={'TUTEL_B200_OVERLAP_ON_CPU': '1'})
+    assert a == c
 
 
 def test_two_ranks_match_single_rank_with_all_experts():

@@ -31,6 +31,12 @@ from ..ops.routing import extract_critical, get_dispatch_count
 from ..parallel import communicate as C
 from ..parallel.overlap import a2a_ffn_overlap_forward
 from ..utils.trace import stage
+
+
+def _OVERLAP_ON_CPU() -> bool:
+    """Testing hook: run the chunked a2a/FFN pipeline (parallel/overlap.py) on CPU tensors too (the reference only
+    pipelines on CUDA, tutel/impls/moe_layer.py:344; on CPU it buys nothing but lets Gloo tests cover the logic)."""
+    return os.environ.get('TUTEL_B200_OVERLAP_ON_CPU', '0') == '1'
 from . import losses
 
 
@@ -329,7 +335,7 @@ class MOELayer(torch.nn.Module):
                         y = y.repeat(1, self.adaptive_degree, 1).view(self.world_size, -1, y.size(2))
                     else:
                         y = y.view(self.world_size, -1, y.size(2))
-                if d > 1 and y.is_cuda:
+                if d > 1 and (y.is_cuda or _OVERLAP_ON_CPU()):
                     with stage('overlap'):
                         y = a2a_ffn_overlap_forward(y, expert_fn=lambda t: self.expert_local(t, reserve_shape),
                                                     a2a_ffn_overlap_degree=d, use_2dh=self.use_2dh, group=self.group)
