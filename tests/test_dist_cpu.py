@@ -173,3 +173,39 @@ def test_two_phase_2dh_all_to_all_equals_flat_on_2x2_ranks():
     """The hierarchical (intra-node then inter-node) exchange - untested in the reference for nnodes > 1."""
     out = run_workers(WORKER_2DH, nproc=4)
     assert 'HIER_OK' in out
+
+
+WORKER_RAGGED = r'''
+sys.path.insert(0, os.getcwd())
+from tutel_b200 import moe, net, system
+env = system.init_data_model_parallel(backend='gloo')
+W, r = env.global_size, env.global_rank
+torch.manual_seed(5)
+layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2, 'capacity_factor': 1.0}, model_dim=16,
+                      experts={'type': 'ffn', 'num_experts_per_device': 2, 'hidden_size_per_expert': 32},
+                      seeds=(1, r + 1, 1))
+# ranks hold different numbers of tokens: capacity must be agreed on through the MAX all-reduce
+torch.manual_seed(50 + r)
+x = torch.randn(24 + 16 * r, 16, requires_grad=True)
+y = layer(x, inequivalent_tokens=True)
+cap = torch.tensor([float(layer.dispatch_count.numel()), float(y.shape[0])])
+assert y.shape == x.shape and torch.isfinite(y).all()
+(y.pow(2).mean() + 0.01 * y.l_aux).backward()
+assert torch.isfinite(x.grad).all()
+# dropless (capacity_factor = 0): capacity = global max expert load, nothing is dropped -> equals a dense evaluation
+y0 = layer(x.detach(), capacity_factor=0, inequivalent_tokens=True)      # gate default cf=1.0 -> 0 falls back; use negative
+yd = layer(x.detach(), capacity_factor=-1000.0, inequivalent_tokens=True)
+ye = layer(x.detach(), capacity_factor=-1000.0, inequivalent_tokens=True, a2a_ffn_overlap_degree=1)
+assert torch.allclose(yd, ye)
+# per-forward top-k override and a second forward with equal token counts still work afterwards
+y1 = layer(x.detach()[:24], top_k=1)
+assert y1.shape == (24, 16)
+net.barrier()
+if r == 0:
+    print('RAGGED_OK')
+'''
+
+
+def test_inequivalent_token_counts_and_dropless_across_ranks():
+    out = run_workers(WORKER_RAGGED, nproc=2)
+    assert 'RAGGED_OK' in out
