@@ -66,48 +66,67 @@ void SymmHeap::open_peers(int rank, const std::vector<std::string>& handles) {
   TB_CUDA_OK(cudaDeviceSynchronize());
 }
 
-void SymmHeap::set_pool(long long off, long long bytes) {
-  std::lock_guard<std::mutex> g(pool_mu_);
-  pool_free_.clear();
-  pool_used_.clear();
-  if (bytes > 0) pool_free_[off] = bytes;
+void BlockPool::reset(long long off, long long bytes) {
+  std::lock_guard<std::mutex> g(mu_);
+  free_.clear();
+  used_.clear();
+  if (bytes > 0) free_[off] = bytes;
 }
 
-long long SymmHeap::pool_alloc(long long bytes) {
+long long BlockPool::alloc(long long bytes) {
   bytes = (bytes + 255) / 256 * 256;
   if (bytes <= 0) bytes = 256;
-  std::lock_guard<std::mutex> g(pool_mu_);
-  for (auto it = pool_free_.begin(); it != pool_free_.end(); ++it) {
+  std::lock_guard<std::mutex> g(mu_);
+  for (auto it = free_.begin(); it != free_.end(); ++it) {
     if (it->second >= bytes) {
       const long long off = it->first, len = it->second;
-      pool_free_.erase(it);
-      if (len > bytes) pool_free_[off + bytes] = len - bytes;
-      pool_used_[off] = bytes;
+      free_.erase(it);
+      if (len > bytes) free_[off + bytes] = len - bytes;
+      used_[off] = bytes;
       return off;
     }
   }
   return -1;
 }
 
-void SymmHeap::pool_free(long long off) {
-  std::lock_guard<std::mutex> g(pool_mu_);
-  auto u = pool_used_.find(off);
-  if (u == pool_used_.end()) return;
+void BlockPool::free(long long off) {
+  std::lock_guard<std::mutex> g(mu_);
+  auto u = used_.find(off);
+  if (u == used_.end()) return;
   long long len = u->second;
-  pool_used_.erase(u);
-  auto next = pool_free_.lower_bound(off);
-  if (next != pool_free_.end() && off + len == next->first) {   // merge with the following free block
+  used_.erase(u);
+  auto next = free_.lower_bound(off);
+  if (next != free_.end() && off + len == next->first) {   // merge with the following free block
     len += next->second;
-    next = pool_free_.erase(next);
+    next = free_.erase(next);
   }
-  if (next != pool_free_.begin()) {                              // merge with the preceding free block
+  if (next != free_.begin()) {                              // merge with the preceding free block
     auto prev = std::prev(next);
     if (prev->first + prev->second == off) {
       prev->second += len;
       return;
     }
   }
-  pool_free_[off] = len;
+  free_[off] = len;
+}
+
+long long BlockPool::free_bytes() {
+  std::lock_guard<std::mutex> g(mu_);
+  long long n = 0;
+  for (auto& kv : free_) n += kv.second;
+  return n;
+}
+
+long long BlockPool::largest_free_block() {
+  std::lock_guard<std::mutex> g(mu_);
+  long long n = 0;
+  for (auto& kv : free_) n = kv.second > n ? kv.second : n;
+  return n;
+}
+
+size_t BlockPool::live_blocks() {
+  std::lock_guard<std::mutex> g(mu_);
+  return used_.size();
 }
 
 void SymmHeap::close() {
@@ -146,6 +165,14 @@ int et_of(at::ScalarType t) {
 
 void register_symm_bindings(pybind11::module& m) {
   namespace py = pybind11;
+  py::class_<tb::BlockPool>(m, "BlockPool")
+      .def(py::init<>())
+      .def("reset", &tb::BlockPool::reset)
+      .def("alloc", &tb::BlockPool::alloc)
+      .def("free", &tb::BlockPool::free)
+      .def("free_bytes", &tb::BlockPool::free_bytes)
+      .def("largest_free_block", &tb::BlockPool::largest_free_block)
+      .def("live_blocks", &tb::BlockPool::live_blocks);
   py::class_<tb::SymmHeap, std::shared_ptr<tb::SymmHeap>>(m, "SymmHeap")
       .def(py::init([](int64_t bytes, int64_t device) {
         return std::make_shared<tb::SymmHeap>(static_cast<size_t>(bytes), static_cast<int>(device));

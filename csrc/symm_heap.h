@@ -11,6 +11,23 @@
 
 namespace tb {
 
+// First-fit block allocator over an offset range (256-byte granularity, adjacent free blocks coalesce).  Owns no
+// memory: the symmetric heap uses it for the receive-buffer pool inside the arena; thread safe.
+class BlockPool {
+ public:
+  void reset(long long off, long long bytes);
+  long long alloc(long long bytes);   // offset of a block of at least `bytes`, -1 when no free block fits
+  void free(long long off);           // unknown offsets are ignored
+  long long free_bytes();
+  long long largest_free_block();
+  size_t live_blocks();
+
+ private:
+  std::mutex mu_;
+  std::map<long long, long long> free_;   // offset -> length of free blocks
+  std::map<long long, long long> used_;   // offset -> length of live blocks
+};
+
 class SymmHeap {
  public:
   SymmHeap(size_t bytes, int device);
@@ -30,9 +47,9 @@ class SymmHeap {
 
   // Receive-buffer pool inside the arena (first-fit free list, 256-byte granularity).  Collectives allocate their
   // output here and hand it out as a tensor whose deleter returns the block - no copy out of a staging area.
-  void set_pool(long long off, long long bytes);
-  long long pool_alloc(long long bytes);   // -1 when no block fits
-  void pool_free(long long off);
+  void set_pool(long long off, long long bytes) { pool_.reset(off, bytes); }
+  long long pool_alloc(long long bytes) { return pool_.alloc(bytes); }   // -1 when no block fits
+  void pool_free(long long off) { pool_.free(off); }
 
  private:
   size_t bytes_ = 0;
@@ -42,9 +59,7 @@ class SymmHeap {
   std::vector<void*> peer_base_;
   unsigned long long* d_peer_table_ = nullptr;
   bool closed_ = false;
-  std::mutex pool_mu_;
-  std::map<long long, long long> pool_free_;   // offset -> length of free blocks
-  std::map<long long, long long> pool_used_;   // offset -> length of live blocks
+  BlockPool pool_;
 };
 
 }  // namespace tb

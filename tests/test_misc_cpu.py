@@ -1,5 +1,7 @@
 """System utilities, compat shim, launcher argument plumbing, activation classification."""
 import os
+
+import pytest
 import subprocess
 import sys
 
@@ -118,3 +120,46 @@ def test_fairseq_style_conversion(monkeypatch):
     p.grad = torch.tensor([1.0, float('inf'), -float('inf')])
     zero_overflow_grads([p], enabled=True)
     assert p.grad.tolist() == [1.0, 0.0, 0.0]
+
+
+def test_block_pool_first_fit_coalescing_and_no_overlap():
+    """csrc/symm_heap.cpp BlockPool: the allocator behind the zero-copy receive buffers of the P2P collectives."""
+    import random
+    from tutel_b200.ops import backend
+    ext = backend.ext()
+    if ext is None or not hasattr(ext, 'BlockPool'):
+        pytest.skip('native extension not built')
+    pool = ext.BlockPool()
+    base, size = 4096, 1 << 20
+    pool.reset(base, size)
+    assert pool.alloc(size + 1) == -1 and pool.free_bytes() == size
+    a = pool.alloc(1)                       # rounded up to the 256-byte granule
+    b = pool.alloc(1000)
+    assert a == base and b == base + 256 and pool.live_blocks() == 2
+    pool.free(a)
+    assert pool.alloc(300) == base + 256 + 1024      # first fit skips the 256-byte hole
+    assert pool.alloc(256) == base                   # ... which an exact fit re-uses
+    pool.free(12345)                                 # unknown offsets are ignored
+    pool.reset(base, size)
+    rng = random.Random(0)
+    live = {}
+    for step in range(4000):
+        if live and (rng.random() < 0.45 or pool.largest_free_block() < 256):
+            off = rng.choice(list(live))
+            pool.free(off)
+            del live[off]
+        else:
+            n = rng.choice([1, 100, 256, 257, 4096, 70000])
+            off = pool.alloc(n)
+            if off < 0:
+                assert pool.largest_free_block() < (n + 255) // 256 * 256
+                continue
+            length = (n + 255) // 256 * 256
+            assert off % 256 == 0 and base <= off and off + length <= base + size
+            for o, l in live.items():
+                assert off + length <= o or o + l <= off, 'blocks overlap'
+            live[off] = length
+        assert pool.free_bytes() == size - sum(live.values()) and pool.live_blocks() == len(live)
+    for off in list(live):
+        pool.free(off)
+    assert pool.free_bytes() == size and pool.largest_free_block() == size      # everything coalesced again
