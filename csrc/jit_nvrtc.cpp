@@ -200,6 +200,13 @@ void invoke(const std::vector<at::Tensor>& tensors, const std::vector<int64_t>& 
 }  // namespace
 
 void register_jit_bindings(pybind11::module& m) {
+  // launch-annotation scanner alone (no compilation): (entry, [grid xyz], [block xyz]) - unit-tested on CPU
+  m.def("jit_parse", [](const std::string& source) {
+    JitKernel k;
+    k.source = source;
+    parse_extents(k);
+    return std::make_tuple(k.entry, std::vector<int>(k.grid, k.grid + 3), std::vector<int>(k.block, k.block + 3));
+  });
   m.def("jit_inject_source", &inject_source);
   m.def("jit_invoke", &invoke);
   m.def("jit_available", [] { return nvrtc().ok; });

@@ -163,3 +163,31 @@ def test_block_pool_first_fit_coalescing_and_no_overlap():
     for off in list(live):
         pool.free(off)
     assert pool.free_bytes() == size and pool.largest_free_block() == size      # everything coalesced again
+
+
+def test_jit_launch_annotation_scanner():
+    """csrc/jit_nvrtc.cpp: `// [thread_extent] blockIdx.x = N` annotations + entry-point detection (reference:
+    tutel/custom/custom_kernel.cpp:174-218 does this with sscanf / strstr)."""
+    from tutel_b200.ops import backend
+    ext = backend.ext()
+    if ext is None or not hasattr(ext, 'jit_parse'):
+        pytest.skip('native extension not built')
+    src = r'''
+      #include <cuda_fp16.h>
+      static __device__ float helper(float v) { return v * 2; }
+      extern "C" __global__ __launch_bounds__(64) void   my_kernel_7(float* __restrict__ x, int n) {
+        // [thread_extent] blockIdx.x = 512
+        // [thread_extent]   threadIdx.x=64
+        // [thread_extent] blockIdx.y = 3
+        // [thread_extent] bogusIdx.x = 9
+        // [thread_extent] threadIdx.z =
+        x[0] = helper(x[0]);
+      }'''
+    entry, grid, block = ext.jit_parse(src)
+    assert entry == 'my_kernel_7' and grid == [512, 3, 1] and block == [64, 1, 1]
+    entry, grid, block = ext.jit_parse('__global__ void k(int*a){}')
+    assert entry == 'k' and grid == [1, 1, 1] and block == [1, 1, 1]
+    with pytest.raises(RuntimeError):
+        ext.jit_parse('void not_a_kernel(int* a) {}')
+    with pytest.raises(RuntimeError):
+        ext.jit_parse('// [thread_extent] blockIdx.x = 4')
