@@ -126,10 +126,14 @@ def main():
     # ---------------- kernel-side number: inputs resident on the device ----------------
     sampler = None
     if rank == 0:
-        sys.path.insert(0, ROOT)
         try:
-            from tutel_b200.utils.timers import ClockSampler   # plain nvidia-smi poller, no kernels involved
-            sampler = ClockSampler(device.index or 0).start()  # started early: nvidia-smi needs a moment to spin up
+            # plain nvidia-smi poller (no kernels, no native code); loaded by file path so that the reference arm's process
+            # never imports the tutel_b200 package
+            import importlib.util
+            spec = importlib.util.spec_from_file_location('_bench_timers', os.path.join(ROOT, 'tutel_b200', 'utils', 'timers.py'))
+            timers = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(timers)
+            sampler = timers.ClockSampler(device.index or 0).start()  # started early: nvidia-smi needs a moment to spin up
         except Exception:  # noqa
             sampler = None
     for _ in range(max(args.warmup, 3)):
