@@ -158,6 +158,10 @@ def engine_for(layer, x: torch.Tensor, crit, d: int):
     from ..models.experts.llama_ffn import LlamaFFNNetwork
     if layer.sharded_count != 1 or layer.adaptive_degree != 1 or layer.megablocks_size > 0:
         return None
+    if not layer.is_postscore and os.environ.get('TUTEL_B200_FUSED_PRESCORE', '0') != '1':
+        # gate-before-experts ("prescore") runs through the same kernels (gates applied in the push, gate gradients from
+        # the combined input gradients) but has no multi-GPU equivalence test yet: generic path unless asked for
+        return None
     if isinstance(ex, FusedExpertsNetwork):
         if ex._act_kind != 'relu' or ex.skip_expert:
             return None
