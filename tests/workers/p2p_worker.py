@@ -67,14 +67,15 @@ def test_collectives(env):
     check('all_to_all autograd', torch.equal(b, a) and torch.equal(a.grad, torch.ones_like(a)))
 
 
-def run_layer(env, fused, dtype, nle, steps=3, overlap=1, model_dim=256, hidden=512, tokens=512, expert='ffn', act=None):
+def run_layer(env, fused, dtype, nle, steps=3, overlap=1, model_dim=256, hidden=512, tokens=512, expert='ffn', act=None,
+              is_postscore=True):
     os.environ['TUTEL_B200_FUSED'] = '1' if fused else '0'
     r, dev = env.global_rank, env.local_device
     torch.manual_seed(7)
     layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2, 'capacity_factor': 1.5}, model_dim=model_dim,
                           experts={'type': expert, 'num_experts_per_device': nle, 'hidden_size_per_expert': hidden,
                                    'activation_fn': act or (lambda t: F.relu(t))},
-                          seeds=(1, r + 1, 1), a2a_ffn_overlap_degree=overlap).to(dev).to(dtype)
+                          seeds=(1, r + 1, 1), a2a_ffn_overlap_degree=overlap, is_postscore=is_postscore).to(dev).to(dtype)
     opt = torch.optim.SGD(layer.parameters(), lr=1e-2)
     torch.manual_seed(50 + r)
     x = torch.randn(tokens, model_dim, device=dev).to(dtype)
@@ -102,6 +103,13 @@ def test_fused_vs_nccl(env):
                 if not ok:
                     print('losses', a[0], b[0], (a[2] - b[2]).abs().max().item(), (a[1] - b[1]).abs().max().item(), flush=True)
                 check('fused==nccl nle=%d d=%d' % (nle, overlap), ok)
+    if os.environ.get('TUTEL_B200_FUSED_PRESCORE', '0') == '1':     # opt-in until it has run once on real GPUs
+        for expert in ('ffn', 'llama_ffn'):
+            a = run_layer(env, True, torch.bfloat16, 1, expert=expert, is_postscore=False)
+            b = run_layer(env, False, torch.bfloat16, 1, expert=expert, is_postscore=False)
+            ok = all(abs(u - v) <= 2e-2 * max(1.0, abs(v)) for u, v in zip(a[0], b[0]))
+            ok = ok and torch.allclose(a[2], b[2], atol=3e-2, rtol=3e-2) and torch.allclose(a[1], b[1], atol=3e-2, rtol=5e-2)
+            check('fused==nccl prescore %s' % expert, ok)
     # gated (SwiGLU) experts through the same engine
     for nle, act in ((1, F.silu), (2, None)):
         a = run_layer(env, True, torch.bfloat16, nle, expert='llama_ffn', act=act)
