@@ -167,6 +167,8 @@ def engine_for(layer, x: torch.Tensor, crit, d: int):
             return None
         if ex.batched_fc1_w.dtype != x.dtype or (layer.model_dim % 8) or (ex.hidden_size % 8) or (ex.output_dim % 8):
             return None
+        if ex.output_dim != layer.model_dim and os.environ.get('TUTEL_B200_FUSED_OUTPUT_DIM', '0') != '1':
+            return None     # `output_dim` experts: supported by the buffers/kernels, not yet covered by a multi-GPU test
     elif isinstance(ex, LlamaFFNNetwork):
         if ex.fp8 or G.classify_activation(ex.activation_fn) not in G.ACT_CODES or ex.W_fc1.dtype != x.dtype:
             return None
