@@ -96,10 +96,13 @@ def main():
     torch.manual_seed(rank)
     x_host = torch.randn([BATCH, TOKENS, args.model_dim], dtype=torch.float32).to(torch.bfloat16).pin_memory()
     y_host = torch.zeros(BATCH, dtype=torch.int64).pin_memory()
-    x_dev, y_dev = x_host.to(device), y_host.to(device)
+    # The layer's input requires a gradient (in a real network the MoE block is never the first layer): the step then
+    # contains all six expert GEMMs - fwd 2, dgrad 2, wgrad 2 - and the input-gradient combine, in BOTH arms.
+    x_dev, y_dev = x_host.to(device).requires_grad_(True), y_host.to(device)
 
     def step(x, y):
         optimizer.zero_grad()
+        x.grad = None
         loss = F.nll_loss(model(x), y)
         loss.backward()
         if world > 1:
@@ -136,9 +139,28 @@ def main():
             sampler = timers.ClockSampler(device.index or 0).start()  # started early: nvidia-smi needs a moment to spin up
         except Exception:  # noqa
             sampler = None
-    for _ in range(max(args.warmup, 3)):
+    first_loss = float(step(x_dev, y_dev).item())          # loss of the very first step (same seeds in both arms)
+    warm_done = 1
+    for _ in range(max(args.warmup, 3) - 1):
         step(x_dev, y_dev)
+        warm_done += 1
     sync()
+    # Keep warming (untimed) until the step time has converged: blocks of 4 steps, stop when two consecutive blocks agree
+    # within 2 % on every rank (clocks, the power-cap controller and the allocator settle within a few dozen steps).
+    prev_blk, warm_trace = None, []
+    for _ in range(12):
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for _ in range(4):
+            step(x_dev, y_dev)
+        w1.record()
+        sync()
+        warm_done += 4
+        blk = maxreduce(w0.elapsed_time(w1) / 4)
+        warm_trace.append(round(blk, 3))
+        if prev_blk is not None and abs(blk - prev_blk) <= 0.02 * prev_blk:
+            break
+        prev_blk = blk
     if args.impl == 'ours':
         launches0 = backend.launch_count()
     t_wall0 = time.time()
@@ -159,43 +181,69 @@ def main():
     # ---------------- end-to-end number: H2D of the step's inputs from pinned memory + D2H of the loss ----------------
     e2e = None
     if not args.no_e2e:
-        xb, yb = torch.empty_like(x_dev), torch.empty_like(y_dev)
-        for _ in range(2):
-            xb.copy_(x_host, non_blocking=True); yb.copy_(y_host, non_blocking=True)
-            float(step(xb, yb).item())
+        # Every step's inputs are copied from pinned host memory (64 MiB + labels) and every step's loss is read back.
+        # The copy for step i+1 is issued on a copy stream before step i is launched (double-buffered input
+        # prefetch, plain torch in both arms), so it overlaps with compute; all `steps` copies are inside the region.
+        copy_stream = torch.cuda.Stream()
+        slots = [(torch.empty_like(x_dev).requires_grad_(True), torch.empty_like(y_dev)) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(i):
+            xb, yb = slots[i % 2]
+            with torch.cuda.stream(copy_stream), torch.no_grad():
+                copy_stream.wait_event(done[i % 2])       # the step that last read this slot has finished
+                xb.copy_(x_host, non_blocking=True)
+                yb.copy_(y_host, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        def run(n):
+            last = None
+            prefetch(0)
+            for i in range(n):
+                if i + 1 < n:
+                    prefetch(i + 1)
+                torch.cuda.current_stream().wait_event(ready[i % 2])
+                loss_i = step(*slots[i % 2])
+                done[i % 2].record()
+                last = float(loss_i.item())               # device -> host read of the step's result
+            return last
+
+        for ev in done:
+            ev.record()
+        run(3)
         sync()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        for _ in range(args.steps):
-            xb.copy_(x_host, non_blocking=True)
-            yb.copy_(y_host, non_blocking=True)
-            last = float(step(xb, yb).item())          # device -> host read of the step's result
+        last = run(args.steps)
         f1.record()
         sync()
         ms_e2e = maxreduce(f0.elapsed_time(f1))
         e2e = {'value': world * BATCH * TOKENS * args.steps / (ms_e2e * 1e-3), 'unit': 'tokens/s',
                'h2d_bytes_per_step': x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size(),
-               'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps, 'last_loss': last}
+               'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps, 'last_loss': last,
+               'input_pipeline': 'double-buffered H2D prefetch on a copy stream (same in both arms)'}
 
     tokens = world * BATCH * TOKENS * args.steps
     value = tokens / (ms * 1e-3)
     mats = 3 if args.expert_type == 'llama_ffn' else 2
-    flops = 2.0 * mats * 3 * BATCH * TOKENS * args.model_dim * args.hidden * min(args.top, args.experts)  # per GPU per step
+    # per GPU per step: `mats` expert GEMMs forward, 2 x `mats` backward (data + weight gradients; x.requires_grad)
+    flops = 2.0 * mats * 3 * BATCH * TOKENS * args.model_dim * args.hidden * min(args.top, args.experts)
     out = {
         'metric': 'moe_layer_fwd_bwd_tokens_per_sec', 'value': value, 'unit': 'tokens/s', 'n_gpus': world,
-        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic (random tokens, random-init weights)',
+        'steps': args.steps, 'warmup': warm_done, 'warmup_requested': args.warmup, 'warmup_ms_per_step_trace': warm_trace, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if not (args.fp8 and args.impl == 'ours') else 'bf16 (fp8 e4m3 expert GEMMs)', 'data': 'synthetic (random tokens, random-init weights)',
         'impl': args.impl,
         'config': {'model': 'helloworld moe_layer top-%d %d-expert %s%s model_dim=%d hidden=%d' % (
             args.top, args.experts, 'ffn(relu)' if args.expert_type == 'ffn' else args.expert_type, ' fp8-forward' if args.fp8 else '', args.model_dim, args.hidden),
                    'global_batch': world * BATCH, 'seq_len': TOKENS, 'tokens_per_gpu': BATCH * TOKENS,
                    'parallelism': 'ep%d (%d local experts/GPU)' % (world, local_experts), 'capacity_factor': 1.0,
-                   'step': 'zero_grad + fwd + nll_loss + bwd + gate-grad all-reduce + SGD',
+                   'step': 'zero_grad + fwd + nll_loss + bwd (incl. input gradient) + gate-grad all-reduce + SGD',
                    'l2': 'working set (weights %.1f GB + activations) exceeds the 126 MB L2; no explicit flush' % (
                        local_experts * 2 * args.model_dim * args.hidden * 2 / 1e9),
                    'a2a_ffn_overlap_degree': args.overlap},
         'tflops_per_gpu': flops / (ms / args.steps * 1e-3) * 1e-12,
-        'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'loss': float(loss.item()),
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'loss': float(loss.item()), 'first_step_loss': first_loss,
     }
     if rank == 0:
         print(json.dumps(out))

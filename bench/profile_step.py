@@ -36,12 +36,13 @@ layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2, 'capacity_factor': 1.0},
 opt = torch.optim.SGD(layer.parameters(), lr=1e-5)
 shared = [p for p in layer.parameters() if not hasattr(p, 'skip_allreduce')]
 torch.manual_seed(rank)
-x = torch.randn(16, 512, 4096, device=dev)
+x = torch.randn(16, 512, 4096, device=dev).requires_grad_(True)      # as in bench.py: the input gradient is part of the step
 y = torch.zeros(16, dtype=torch.int64, device=dev)
 
 
 def step():
     opt.zero_grad()
+    x.grad = None
     loss = F.nll_loss(F.log_softmax(torch.sum(layer(x), dim=2), dim=1), y)
     loss.backward()
     if world > 1:

@@ -215,46 +215,88 @@ at::Tensor gate_grad(const at::Tensor& a, const at::Tensor& buf, const at::Tenso
   return out;
 }
 
-std::vector<at::Tensor> gate_topk_forward(const at::Tensor& logits, int64_t k) {
-  TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == at::kFloat && logits.dim() == 2 && logits.is_contiguous());
+// logits [S, E] (fp32 / fp16 / bf16) -> [scores fp32 [S,E], idx int [k,S], top fp32 [k,S], gates fp32 [k,S], loc int [k,S],
+// counts int [E], ce fp32 [E], l_aux (scalar, logits dtype), slot_src int [E*C] (only when C > 0)]   - two launches
+std::vector<at::Tensor> gate_route_forward(const at::Tensor& logits, int64_t k, int64_t C, bool normalize, double eps) {
+  TORCH_CHECK(logits.is_cuda() && logits.dim() == 2 && logits.is_contiguous(), "gate_route_forward: contiguous CUDA [S, E] logits expected");
   const c10::cuda::CUDAGuard guard(logits.device());
   const int S = static_cast<int>(logits.size(0)), E = static_cast<int>(logits.size(1));
-  const int nblk = (S + 255) / 256;
-  at::Tensor scores = at::empty_like(logits);
-  at::Tensor idx = at::empty({k, S}, logits.options().dtype(at::kInt));
-  at::Tensor top = at::empty({k, S}, logits.options());
-  at::Tensor me = at::empty({nblk, E}, logits.options());
-  at::Tensor ce = at::empty({nblk, E}, logits.options().dtype(at::kInt));
-  TB_CHECK_CUDA(tb::gate_topk_forward(logits.data_ptr<float>(), scores.data_ptr<float>(), idx.data_ptr<int>(),
-                                      top.data_ptr<float>(), me.data_ptr<float>(), ce.data_ptr<int>(), S, E,
-                                      static_cast<int>(k), cur_stream()));
-  return {scores, idx, top, me, ce};
+  TORCH_CHECK(E <= 512 && k >= 1 && k <= 32 && k <= E, "gate_route_forward: needs E <= 512 and 1 <= k <= min(32, E)");
+  const int tiles = tb::gate_route_tiles(S);
+  auto f32 = logits.options().dtype(at::kFloat);
+  auto i32 = logits.options().dtype(at::kInt);
+  at::Tensor scores = at::empty({S, E}, f32);
+  at::Tensor idx = at::empty({k, S}, i32), loc = at::empty({k, S}, i32), counts = at::empty({E}, i32);
+  at::Tensor top = at::empty({k, S}, f32), gates = at::empty({k, S}, f32), ce = at::empty({E}, f32);
+  at::Tensor l_aux = at::empty({}, logits.options());
+  at::Tensor me = at::empty({tiles, E}, f32);
+  at::Tensor hist = at::empty({tiles, k, E}, i32);
+  at::Tensor slot;
+  if (C > 0) slot = at::empty({E * C}, i32);
+  TB_CHECK_CUDA(tb::gate_route_forward(logits.data_ptr(), scores.data_ptr<float>(), idx.data_ptr<int>(), top.data_ptr<float>(),
+                                       gates.data_ptr<float>(), me.data_ptr<float>(), hist.data_ptr<int>(), loc.data_ptr<int>(),
+                                       counts.data_ptr<int>(), C > 0 ? slot.data_ptr<int>() : nullptr, ce.data_ptr<float>(),
+                                       l_aux.data_ptr(), S, E, static_cast<int>(k), static_cast<int>(C), normalize,
+                                       static_cast<float>(eps), elem_type_of(logits), cur_stream()));
+  std::vector<at::Tensor> out{scores, idx, top, gates, loc, counts, ce, l_aux};
+  if (C > 0) out.push_back(slot);
+  return out;
 }
 
-at::Tensor gate_topk_backward(const at::Tensor& scores, const at::Tensor& idx, const at::Tensor& top,
-                              const at::Tensor& dgates, const c10::optional<at::Tensor>& ce,
-                              const c10::optional<at::Tensor>& dl, bool normalize, double eps) {
+// -> d logits [S, E] in `like`'s dtype; dgates fp32 [k, S] or None; dl: scalar of `like`'s dtype or None      - one launch
+at::Tensor gate_route_backward(const at::Tensor& scores, const at::Tensor& idx, const at::Tensor& top,
+                               const c10::optional<at::Tensor>& dgates, const c10::optional<at::Tensor>& ce,
+                               const c10::optional<at::Tensor>& dl, const at::Tensor& like, bool normalize, double eps) {
   TORCH_CHECK(scores.is_cuda() && scores.scalar_type() == at::kFloat && scores.dim() == 2 && scores.is_contiguous());
   const int S = static_cast<int>(scores.size(0)), E = static_cast<int>(scores.size(1));
   const int k = static_cast<int>(idx.size(0));
   TORCH_CHECK(idx.scalar_type() == at::kInt && idx.is_contiguous() && idx.size(1) == S);
   TORCH_CHECK(top.scalar_type() == at::kFloat && top.is_contiguous() && top.sizes() == idx.sizes());
-  TORCH_CHECK(dgates.scalar_type() == at::kFloat && dgates.is_contiguous() && dgates.sizes() == idx.sizes());
+  const float* dg_p = nullptr;
   const float* ce_p = nullptr;
-  const float* dl_p = nullptr;
-  if (ce.has_value() && ce->defined()) {
-    TORCH_CHECK(ce->is_cuda() && ce->scalar_type() == at::kFloat && ce->is_contiguous() && ce->numel() == E);
-    ce_p = ce->data_ptr<float>();
+  const void* dl_p = nullptr;
+  if (dgates.has_value() && dgates->defined()) {
+    TORCH_CHECK(dgates->scalar_type() == at::kFloat && dgates->is_contiguous() && dgates->sizes() == idx.sizes());
+    dg_p = dgates->data_ptr<float>();
   }
-  if (dl.has_value() && dl->defined()) {
-    TORCH_CHECK(dl->is_cuda() && dl->scalar_type() == at::kFloat && dl->numel() == 1);
-    dl_p = dl->data_ptr<float>();
+  if (ce.has_value() && ce->defined() && dl.has_value() && dl->defined()) {
+    TORCH_CHECK(ce->is_cuda() && ce->scalar_type() == at::kFloat && ce->is_contiguous() && ce->numel() == E);
+    TORCH_CHECK(dl->is_cuda() && dl->scalar_type() == like.scalar_type() && dl->numel() == 1);
+    ce_p = ce->data_ptr<float>();
+    dl_p = dl->data_ptr();
   }
   const c10::cuda::CUDAGuard guard(scores.device());
-  at::Tensor out = at::empty_like(scores);
-  TB_CHECK_CUDA(tb::gate_topk_backward(scores.data_ptr<float>(), idx.data_ptr<int>(), top.data_ptr<float>(),
-                                       dgates.data_ptr<float>(), ce_p, dl_p, out.data_ptr<float>(), S, E, k, normalize,
-                                       static_cast<float>(eps), cur_stream()));
+  at::Tensor out = at::empty({S, E}, like.options());
+  TB_CHECK_CUDA(tb::gate_route_backward(scores.data_ptr<float>(), idx.data_ptr<int>(), top.data_ptr<float>(), dg_p, ce_p, dl_p,
+                                        out.data_ptr(), S, E, k, normalize, static_cast<float>(eps), elem_type_of(like),
+                                        cur_stream()));
+  return out;
+}
+
+// x [G, T, N] (last dim contiguous) -> [G, N] column sums in x's dtype (fp32 accumulation)
+at::Tensor grouped_colsum(const at::Tensor& x) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 3 && x.stride(2) == 1, "grouped_colsum: CUDA [G, T, N] tensor expected");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int G = static_cast<int>(x.size(0)), T = static_cast<int>(x.size(1)), N = static_cast<int>(x.size(2));
+  const int splits = tb::colsum_row_splits(G, T, N, static_cast<int>(x.element_size()));
+  at::Tensor out = at::empty({G, N}, x.options());
+  at::Tensor acc;
+  if (splits > 1) acc = at::zeros({G, N}, x.options().dtype(at::kFloat));
+  TB_CHECK_CUDA(tb::grouped_colsum(x.data_ptr(), x.stride(1), x.stride(0), out.data_ptr(),
+                                   splits > 1 ? acc.data_ptr<float>() : nullptr, G, T, N, splits, elem_type_of(x), cur_stream()));
+  if (splits > 1) out.copy_(acc);
+  return out;
+}
+
+// int [S, E] -> cumsum along dim 0 minus one (int32)
+at::Tensor cumsum_sub_one(const at::Tensor& data) {
+  TORCH_CHECK(data.is_cuda() && data.dim() == 2, "cumsum_sub_one: CUDA [S, E] tensor expected");
+  const c10::cuda::CUDAGuard guard(data.device());
+  at::Tensor x = data.to(at::kInt).contiguous();
+  const int S = static_cast<int>(x.size(0)), E = static_cast<int>(x.size(1));
+  at::Tensor out = at::empty_like(x);
+  at::Tensor ws = at::empty({static_cast<int64_t>(tb::cumsum_workspace_ints(S, E))}, x.options());
+  TB_CHECK_CUDA(tb::cumsum_sub_one(x.data_ptr<int>(), out.data_ptr<int>(), ws.data_ptr<int>(), S, E, cur_stream()));
   return out;
 }
 
@@ -389,8 +431,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("encode_rows", &encode_rows);
   m.def("decode_rows", &decode_rows);
   m.def("gate_grad", &gate_grad);
-  m.def("gate_topk_forward", &gate_topk_forward);
-  m.def("gate_topk_backward", &gate_topk_backward);
+  m.def("gate_route_forward", &gate_route_forward);
+  m.def("gate_route_backward", &gate_route_backward);
+  m.def("grouped_colsum", &grouped_colsum);
+  m.def("cumsum_sub_one", &cumsum_sub_one);
   m.def("skinny_gemm", &skinny_gemm);
   m.def("quantize_rows", &quantize_rows);
   register_symm_bindings(m);

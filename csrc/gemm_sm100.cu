@@ -1098,4 +1098,9 @@ cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const c
   return cudaErrorInvalidValue;
 }
 
+// run-time spin-wait limit of this translation unit's kernels (ptx.cuh)
+cudaError_t set_spin_timeout_gemm(unsigned long long ns) {
+  return cudaMemcpyToSymbol(tb_spin_timeout_ns, &ns, sizeof(ns));
+}
+
 }  // namespace tb

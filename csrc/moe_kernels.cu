@@ -395,149 +395,6 @@ gate_grad_kernel(const T* __restrict__ a, const T* __restrict__ buf, const int* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// fused gating forward: softmax + top-k + aux-loss partial sums, one warp per token
-// ------------------------------------------------------------------------------------------------
-template <int VPT>
-__global__ void __launch_bounds__(256)
-gate_topk_kernel(const float* __restrict__ logits, float* __restrict__ scores, int* __restrict__ idx,
-                 float* __restrict__ topk_scores, float* __restrict__ me_partial, int* __restrict__ ce_partial, int S,
-                 int E, int k, int tokens_per_block) {
-  __shared__ float sm_me[8][32 * VPT];
-  __shared__ int sm_ce[8][32 * VPT];
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  float me[VPT];
-  int ce[VPT];
-#pragma unroll
-  for (int i = 0; i < VPT; ++i) { me[i] = 0.0f; ce[i] = 0; }
-  const long long s_begin = static_cast<long long>(blockIdx.x) * tokens_per_block;
-  const long long s_end = min(s_begin + tokens_per_block, static_cast<long long>(S));
-  for (long long s = s_begin + warp; s < s_end; s += 8) {
-    float v[VPT];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-      const int e = lane + 32 * i;
-      v[i] = e < E ? logits[s * E + e] : -INFINITY;
-      mx = fmaxf(mx, v[i]);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.0f;
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-      v[i] = (lane + 32 * i < E) ? expf(v[i] - mx) : 0.0f;
-      sum += v[i];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = 1.0f / sum;
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-      const int e = lane + 32 * i;
-      v[i] *= inv;
-      if (e < E) {
-        scores[s * E + e] = v[i];
-        me[i] += v[i];
-      }
-    }
-    // iterative arg-max, ties broken towards the lower expert id
-    unsigned taken = 0;  // bit i: this lane's i-th value already selected
-    for (int j = 0; j < k; ++j) {
-      float best = -1.0f;
-      int best_e = 0x7fffffff;
-#pragma unroll
-      for (int i = 0; i < VPT; ++i) {
-        const int e = lane + 32 * i;
-        if (e < E && !((taken >> i) & 1u) && (v[i] > best)) { best = v[i]; best_e = e; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oe = __shfl_xor_sync(0xffffffffu, best_e, o);
-        if (ob > best || (ob == best && oe < best_e)) { best = ob; best_e = oe; }
-      }
-      if ((best_e & 31) == lane && best_e < E) {
-        taken |= 1u << (best_e >> 5);
-        if (j == 0) ce[best_e >> 5] += 1;
-      }
-      if (lane == 0) {
-        idx[static_cast<long long>(j) * S + s] = best_e;
-        topk_scores[static_cast<long long>(j) * S + s] = best;
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < VPT; ++i) { sm_me[warp][lane + 32 * i] = me[i]; sm_ce[warp][lane + 32 * i] = ce[i]; }
-  __syncthreads();
-  for (int e = threadIdx.x; e < E; e += 256) {
-    float a = 0.0f;
-    int c = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) { a += sm_me[w][e]; c += sm_ce[w][e]; }
-    me_partial[static_cast<long long>(blockIdx.x) * E + e] = a;
-    ce_partial[static_cast<long long>(blockIdx.x) * E + e] = c;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// fused gating backward: d logits from the gradients of the (normalised) top-k gates and of the GShard auxiliary
-// loss, one warp per token:
-//   r_j  = p[idx_j]                       raw top-k scores,      D = sum_j r_j,  Dc = max(D, eps)
-//   g_j  = r_j / Dc   (normalize && k>1)  ->  dr_j = dg_j / Dc - [D > eps] * (sum_i dg_i r_i) / Dc^2
-//   dp_e = dl * ce_e * E / S^2 + sum_j [idx_j == e] dr_j          (l_aux = E / S^2 * sum_e me_e * ce_e, ce constant)
-//   dlogit_e = p_e * (dp_e - sum_e' dp_e' p_e')                   (softmax)
-// ------------------------------------------------------------------------------------------------
-template <int VPT>
-__global__ void __launch_bounds__(256)
-gate_topk_bwd_kernel(const float* __restrict__ scores, const int* __restrict__ idx, const float* __restrict__ topk_scores,
-                     const float* __restrict__ dgates, const float* __restrict__ ce, const float* __restrict__ dl,
-                     float* __restrict__ dlogits, int S, int E, int k, int normalize, float eps) {
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const float aux_scale = (dl != nullptr ? dl[0] : 0.0f) * static_cast<float>(E) /
-                          (static_cast<float>(S) * static_cast<float>(S));
-  for (long long s = static_cast<long long>(blockIdx.x) * 8 + warp; s < S; s += static_cast<long long>(gridDim.x) * 8) {
-    float p[VPT], dp[VPT];
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-      const int e = lane + 32 * i;
-      p[i] = e < E ? scores[s * E + e] : 0.0f;
-      dp[i] = (e < E && ce != nullptr) ? aux_scale * ce[e] : 0.0f;
-    }
-    // every lane reads the k (<= 32) choices of this token redundantly: tiny and L1-resident
-    float D = 0.0f, dot = 0.0f;
-    for (int j = 0; j < k; ++j) {
-      const float r = topk_scores[static_cast<long long>(j) * S + s];
-      D += r;
-      dot += dgates[static_cast<long long>(j) * S + s] * r;
-    }
-    const bool norm = normalize != 0 && k > 1;
-    const float Dc = fmaxf(D, eps);
-    for (int j = 0; j < k; ++j) {
-      const int e = idx[static_cast<long long>(j) * S + s];
-      float dr = dgates[static_cast<long long>(j) * S + s];
-      if (norm) dr = dr / Dc - (D > eps ? dot / (Dc * Dc) : 0.0f);
-      if (e >= 0 && (e & 31) == lane) {
-#pragma unroll
-        for (int i = 0; i < VPT; ++i)
-          if (i == (e >> 5)) dp[i] += dr;
-      }
-    }
-    float acc = 0.0f;
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) acc += dp[i] * p[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-      const int e = lane + 32 * i;
-      if (e < E) dlogits[s * E + e] = p[i] * (dp[i] - acc);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // per-row e4m3 quantisation (activations / K-major weights for the fp8 tcgen05 GEMM): one warp per row
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -742,41 +599,9 @@ cudaError_t quantize_rows_e4m3(const void* x, void* q, float* scale, long long R
   return cudaGetLastError();
 }
 
-cudaError_t gate_topk_forward(const float* logits, float* scores, int* idx, float* topk_scores, float* me_partial,
-                              int* ce_partial, int S, int E, int k, cudaStream_t stream) {
-  if (S <= 0) return cudaSuccess;
-  const int tokens_per_block = 256;
-  const int grid = (S + tokens_per_block - 1) / tokens_per_block;
-#define TB_GATE(VPTv)                                                                                              \
-  gate_topk_kernel<VPTv><<<grid, 256, 0, stream>>>(logits, scores, idx, topk_scores, me_partial, ce_partial, S, E, k, \
-                                                   tokens_per_block)
-  if (E <= 32) TB_GATE(1);
-  else if (E <= 64) TB_GATE(2);
-  else if (E <= 128) TB_GATE(4);
-  else if (E <= 256) TB_GATE(8);
-  else if (E <= 512) TB_GATE(16);
-  else return cudaErrorInvalidValue;
-#undef TB_GATE
-  return cudaGetLastError();
-}
-
-cudaError_t gate_topk_backward(const float* scores, const int* idx, const float* topk_scores, const float* dgates,
-                               const float* ce, const float* dl, float* dlogits, int S, int E, int k, bool normalize,
-                               float eps, cudaStream_t stream) {
-  if (S <= 0) return cudaSuccess;
-  const long long want_blocks = (static_cast<long long>(S) + 7) / 8;
-  const int grid = static_cast<int>(want_blocks < 4LL * num_sms() ? want_blocks : 4LL * num_sms());
-#define TB_GATE_BWD(VPTv)                                                                                          \
-  gate_topk_bwd_kernel<VPTv><<<grid, 256, 0, stream>>>(scores, idx, topk_scores, dgates, ce, dl, dlogits, S, E, k,   \
-                                                       normalize ? 1 : 0, eps)
-  if (E <= 32) TB_GATE_BWD(1);
-  else if (E <= 64) TB_GATE_BWD(2);
-  else if (E <= 128) TB_GATE_BWD(4);
-  else if (E <= 256) TB_GATE_BWD(8);
-  else if (E <= 512) TB_GATE_BWD(16);
-  else return cudaErrorInvalidValue;
-#undef TB_GATE_BWD
-  return cudaGetLastError();
+// run-time spin-wait limit of this translation unit's kernels (ptx.cuh)
+cudaError_t set_spin_timeout_moe(unsigned long long ns) {
+  return cudaMemcpyToSymbol(tb_spin_timeout_ns, &ns, sizeof(ns));
 }
 
 }  // namespace tb

@@ -5,7 +5,7 @@
 
 namespace tb {
 
-enum ElemType : int { ET_F32 = 0, ET_F16 = 1, ET_BF16 = 2 };
+enum ElemType : int { ET_F32 = 0, ET_F16 = 1, ET_BF16 = 2, ET_I32 = 3, ET_I64 = 4 };
 
 // Stable slot assignment.  idx: [k, S] int32 expert id of the j-th choice of token s (or <0 = none).
 // Produces loc[k, S] (position of the token inside its expert's queue: all 1st choices in token order, then all
@@ -43,16 +43,36 @@ cudaError_t decode_rows(const void* buf, const void* gates, const int* idx, cons
 cudaError_t gate_grad(const void* a, const void* buf, const int* idx, const int* loc, void* dgate, int S, int E,
                       int k, int C, int M, int elem_type, cudaStream_t stream);
 
-// Fused gating forward: logits[S,E] (fp32) -> softmax scores, top-k ids, raw top-k scores, and the per-expert
-// partial sums needed by the GShard auxiliary loss, one warp per token.
-cudaError_t gate_topk_forward(const float* logits, float* scores, int* idx, float* topk_scores, float* me_partial,
-                              int* ce_partial, int S, int E, int k, cudaStream_t stream);
+// ---- fused gating + routing (gate_route.cu) ---------------------------------------------------------------------
+// Two launches: logits [S,E] (fp32/fp16/bf16) -> softmax scores (fp32), top-k ids idx[k,S], raw top-k scores top[k,S],
+// normalised gates[k,S] (fp32), queue locations loc[k,S], per-expert counts[E], the inverse slot map slot_src[E*C]
+// (optional: pass null / C = 0 when the capacity is not known yet), first-choice counts ce[E] (fp32) and the GShard
+// auxiliary loss l_aux (scalar of the logits' dtype, optional).  Workspaces: me_partial float[tiles*E], hist
+// int[tiles*k*E] with tiles = gate_route_tiles(S).  Limits: E <= 512, k <= 32.
+int gate_route_tiles(int S);
+cudaError_t gate_route_forward(const void* logits, float* scores, int* idx, float* top, float* gates, float* me_partial,
+                               int* hist, int* loc, int* counts, int* slot_src, float* ce_out, void* l_aux, int S, int E,
+                               int k, int C, bool normalize, float eps, int elem_type, cudaStream_t stream);
+// One launch: d logits [S,E] (dtype of the logits) from dgates fp32 [k,S] (may be null) and the loss gradient `dl`
+// (device scalar of the logits' dtype, may be null; needs ce).
+cudaError_t gate_route_backward(const float* scores, const int* idx, const float* top, const float* dgates,
+                                const float* ce, const void* dl, void* dlogits, int S, int E, int k, bool normalize,
+                                float eps, int elem_type, cudaStream_t stream);
 
-// Fused gating backward (see the kernel for the formulas): gradients of the normalised top-k gates [k,S] and of the
-// GShard loss (device scalar `dl`, may be null) -> d logits [S,E].  `ce` = first-choice counts per expert (fp32 [E]).
-cudaError_t gate_topk_backward(const float* scores, const int* idx, const float* topk_scores, const float* dgates,
-                               const float* ce, const float* dl, float* dlogits, int S, int E, int k, bool normalize,
-                               float eps, cudaStream_t stream);
+// out[g, n] = sum_r x[g, r, n]  (bias gradients).  splits = colsum_row_splits(..): 1 -> results are written to `out`
+// (dtype of x); > 1 -> partial sums are atomically added to the zero-initialised fp32 buffer `acc` [G, N].
+int colsum_row_splits(int G, int rows, int N, int elem_bytes);
+cudaError_t grouped_colsum(const void* x, long long ld, long long group_stride, void* out, float* acc, int G, int rows,
+                           int N, int splits, int elem_type, cudaStream_t stream);
+
+// out[s, e] = (sum_{s' <= s} in[s', e]) - 1   (`tutel_ops.cumsum`, tutel/custom/custom_kernel.cpp:822-872)
+size_t cumsum_workspace_ints(int S, int E);
+cudaError_t cumsum_sub_one(const int* in, int* out, int* workspace, int S, int E, cudaStream_t stream);
+
+// runtime spin-wait limit of the cross-GPU protocols (per translation unit; bindings call all of them)
+cudaError_t set_spin_timeout_moe(unsigned long long ns);
+cudaError_t set_spin_timeout_p2p(unsigned long long ns);
+cudaError_t set_spin_timeout_gemm(unsigned long long ns);
 
 // q[r, :] = e4m3(x[r, :] / scale[r]),  scale[r] = max|x[r, :]| / 448   (one scale per row; rows are K-major GEMM
 // operands, so the scale factors out of the dot product and is applied in the GEMM epilogue).

@@ -119,6 +119,92 @@ p2p_reduce_slice_kernel(T* __restrict__ out, const unsigned long long* __restric
   }
 }
 
+// ---- one-shot all-reduce ---------------------------------------------------------------------------------
+template <typename T> struct RedT;
+template <> struct RedT<float> { using Acc = float; static __device__ float up(float v) { return v; } static __device__ float down(float v) { return v; } };
+template <> struct RedT<__half> { using Acc = float; static __device__ float up(__half v) { return __half2float(v); } static __device__ __half down(float v) { return __float2half_rn(v); } };
+template <> struct RedT<__nv_bfloat16> { using Acc = float; static __device__ float up(__nv_bfloat16 v) { return __bfloat162float(v); } static __device__ __nv_bfloat16 down(float v) { return __float2bfloat16_rn(v); } };
+template <> struct RedT<int> { using Acc = int; static __device__ int up(int v) { return v; } static __device__ int down(int v) { return v; } };
+template <> struct RedT<long long> { using Acc = long long; static __device__ long long up(long long v) { return v; } static __device__ long long down(long long v) { return v; } };
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+p2p_allreduce_oneshot_kernel(const T* __restrict__ in, T* __restrict__ out,
+                             const unsigned long long* __restrict__ peer_table, long long inbox_off, long long slot_bytes,
+                             long long flag_off, long long n, int rank, int world, uint32_t epoch, bool is_max) {
+  using Acc = typename RedT<T>::Acc;
+  const int parity = static_cast<int>(epoch & 1u);
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long per_al = (per * static_cast<long long>(sizeof(T)) + 15) / 16 * 16 / static_cast<long long>(sizeof(T));
+  const long long i0 = per_al * blockIdx.x;
+  const long long i1 = min(n, i0 + per_al);
+  // (1) my chunk -> slot [parity][rank] of every peer's inbox (own inbox included: the reduction reads W uniform slots)
+  if (i0 < i1) {
+    const long long nb = (i1 - i0) * static_cast<long long>(sizeof(T));
+    const uint8_t* s = reinterpret_cast<const uint8_t*>(in + i0);
+    const bool vec = ((reinterpret_cast<uintptr_t>(s) & 15) == 0);
+    for (int q = 0; q < world; ++q) {
+      const int p = (rank + q) % world;
+      uint8_t* d = reinterpret_cast<uint8_t*>(peer_table[p]) + inbox_off +
+                   (static_cast<long long>(parity) * world + rank) * slot_bytes + i0 * static_cast<long long>(sizeof(T));
+      if (vec) {
+        const long long nv = nb >> 4;
+        for (long long v = threadIdx.x; v < nv; v += blockDim.x)
+          ptx::st_na_v4(reinterpret_cast<uint4*>(d) + v, ptx::ld_nc_v4(reinterpret_cast<const uint4*>(s) + v));
+        for (long long b = (nv << 4) + threadIdx.x; b < nb; b += blockDim.x) d[b] = s[b];
+      } else {
+        for (long long b = threadIdx.x; b < nb; b += blockDim.x) d[b] = s[b];
+      }
+    }
+  }
+  __syncthreads();
+  // (2) publish: one flag per (source rank, block) on every peer;  (3) wait for the W flags of this block
+  if (threadIdx.x < world) {
+    const int p = threadIdx.x;
+    uint32_t* f = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(peer_table[p]) + flag_off) +
+                  (static_cast<long long>(parity) * world + rank) * kOneShotMaxBlocks + blockIdx.x;
+    ptx::fence_acq_rel_sys();
+    ptx::st_release_sys(f, epoch);
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(peer_table[rank]) + flag_off) +
+                           (static_cast<long long>(parity) * world + p) * kOneShotMaxBlocks + blockIdx.x;
+    ptx::wait_flag_ge_sys(mine, epoch);
+  }
+  __syncthreads();
+  // (4) reduce the W copies in rank order
+  const uint8_t* inbox = reinterpret_cast<const uint8_t*>(peer_table[rank]) + inbox_off +
+                         static_cast<long long>(parity) * world * slot_bytes;
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    Acc acc = RedT<T>::up(*reinterpret_cast<const volatile T*>(inbox + i * static_cast<long long>(sizeof(T))));
+    for (int p = 1; p < world; ++p) {
+      const Acc v = RedT<T>::up(*reinterpret_cast<const volatile T*>(inbox + p * slot_bytes + i * static_cast<long long>(sizeof(T))));
+      acc = is_max ? (v > acc ? v : acc) : acc + v;
+    }
+    out[i] = RedT<T>::down(acc);
+  }
+}
+
+// ---- 2-D hierarchical all-to-all: record transpose between the two phases ---------------------------------------
+__global__ void __launch_bounds__(256)
+p2p_stride_copy_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int rows, int cols, long long width) {
+  const long long records = static_cast<long long>(rows) * cols;
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | static_cast<uintptr_t>(width)) & 15) == 0;
+  for (long long i = blockIdx.y; i < records; i += gridDim.y) {
+    const long long r = i / cols, c = i - r * cols;
+    const uint8_t* s = src + i * width;
+    uint8_t* d = dst + (c * rows + r) * width;
+    if (vec) {
+      const long long nv = width >> 4;
+      for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nv;
+           v += static_cast<long long>(gridDim.x) * blockDim.x)
+        ptx::st_na_v4(reinterpret_cast<uint4*>(d) + v, ptx::ld_nc_v4(reinterpret_cast<const uint4*>(s) + v));
+    } else {
+      for (long long b = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; b < width;
+           b += static_cast<long long>(gridDim.x) * blockDim.x)
+        d[b] = s[b];
+    }
+  }
+}
+
 __global__ void p2p_barrier_kernel(const unsigned long long* __restrict__ peer_table, long long bar_off, int rank,
                                    int world, uint32_t epoch) {
   const int p = threadIdx.x;
@@ -169,10 +255,52 @@ cudaError_t p2p_reduce_slice(void* out, const unsigned long long* peer_table, lo
   return cudaGetLastError();
 }
 
+cudaError_t p2p_allreduce_oneshot(const void* in, void* out, const unsigned long long* peer_table, long long inbox_off,
+                                  long long slot_bytes, long long flag_off, long long n_elems, int elem_type, int rank,
+                                  int world, uint32_t epoch, bool is_max, cudaStream_t stream) {
+  if (n_elems <= 0) return cudaSuccess;
+  if (world > kMaxPeers) return cudaErrorInvalidValue;
+  const int es = elem_type == ET_F32 || elem_type == ET_I32 ? 4 : (elem_type == ET_I64 ? 8 : 2);
+  const long long bytes = n_elems * es;
+  if (bytes > slot_bytes) return cudaErrorInvalidValue;
+  long long want = (bytes + 4095) / 4096;            // 256 threads x 16 B per block and pass
+  const int grid = static_cast<int>(want < 1 ? 1 : (want > kOneShotMaxBlocks ? kOneShotMaxBlocks : want));
+#define TB_ONESHOT(T)                                                                                                   \
+  p2p_allreduce_oneshot_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(in), static_cast<T*>(out), peer_table, \
+                                                            inbox_off, slot_bytes, flag_off, n_elems, rank, world, epoch, \
+                                                            is_max)
+  switch (elem_type) {
+    case ET_F32: TB_ONESHOT(float); break;
+    case ET_F16: TB_ONESHOT(__half); break;
+    case ET_BF16: TB_ONESHOT(__nv_bfloat16); break;
+    case ET_I32: TB_ONESHOT(int); break;
+    case ET_I64: TB_ONESHOT(long long); break;
+    default: return cudaErrorInvalidValue;
+  }
+#undef TB_ONESHOT
+  return cudaGetLastError();
+}
+
+cudaError_t p2p_stride_copy(const void* src, void* dst, int rows, int cols, long long width_bytes, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0 || width_bytes <= 0) return cudaSuccess;
+  const long long records = static_cast<long long>(rows) * cols;
+  const long long per = (width_bytes / 16 + 255) / 256;
+  dim3 grid(static_cast<unsigned>(per < 1 ? 1 : (per > 64 ? 64 : per)), static_cast<unsigned>(records < 4096 ? records : 4096));
+  p2p_stride_copy_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), rows, cols,
+                                                   width_bytes);
+  return cudaGetLastError();
+}
+
+
 cudaError_t p2p_barrier(const unsigned long long* peer_table, long long bar_off, int rank, int world, uint32_t epoch,
                         cudaStream_t stream) {
   p2p_barrier_kernel<<<1, 32, 0, stream>>>(peer_table, bar_off, rank, world, epoch);
   return cudaGetLastError();
+}
+
+// run-time spin-wait limit of this translation unit's kernels (ptx.cuh)
+cudaError_t set_spin_timeout_p2p(unsigned long long ns) {
+  return cudaMemcpyToSymbol(tb_spin_timeout_ns, &ns, sizeof(ns));
 }
 
 }  // namespace tb

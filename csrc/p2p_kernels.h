@@ -34,6 +34,22 @@ cudaError_t p2p_reduce_slice(void* out, const unsigned long long* peer_table, lo
                              long long slice_off_bytes, long long n_elems, int elem_type, int rank, int world,
                              bool is_max, cudaStream_t stream);
 
+// One-shot all-reduce in ONE launch (small tensors: gate gradients, capacity maxima, scalars).  Every rank stores its
+// input into slot [parity][rank] of EVERY peer's inbox (16-byte NVLink stores), publishes one flag per (source, block)
+// with st.release.sys, waits for the W flags of its own block and reduces the W copies in rank order (so all ranks
+// obtain bit-identical results).  Inbox: heap offset inbox_off, 2 x W x slot_bytes;  flags: uint32 at flag_off,
+// 2 x W x kOneShotMaxBlocks.  `epoch` = 1-based call number on this inbox (parity = epoch & 1); successive calls must
+// be issued on one stream.  in/out may alias.  Supported: fp32/fp16/bf16 (fp32 accumulate), int32, int64; SUM and MAX.
+constexpr int kOneShotMaxBlocks = 64;
+cudaError_t p2p_allreduce_oneshot(const void* in, void* out, const unsigned long long* peer_table, long long inbox_off,
+                                  long long slot_bytes, long long flag_off, long long n_elems, int elem_type, int rank,
+                                  int world, uint32_t epoch, bool is_max, cudaStream_t stream);
+
+// dst[(i % rows) * cols + i / rows, :] = src[i, :] for i in [0, rows*cols): the [rows, cols] -> [cols, rows] block
+// transpose of `width`-byte records that re-orders all-to-all payloads between the intra-node and the inter-node phase
+// of the 2-D hierarchical exchange (reference: the stride-copy kernel of tutel/custom/custom_kernel.cpp:408-429).
+cudaError_t p2p_stride_copy(const void* src, void* dst, int rows, int cols, long long width_bytes, cudaStream_t stream);
+
 // All ranks arrive and wait (system-scope release/acquire); `epoch` 1-based per counter array at bar_off (uint32[W]).
 cudaError_t p2p_barrier(const unsigned long long* peer_table, long long bar_off, int rank, int world, uint32_t epoch,
                         cudaStream_t stream);

@@ -8,8 +8,14 @@
 #include <cuda_runtime.h>
 
 #ifndef TB_SPIN_TIMEOUT_NS
-#define TB_SPIN_TIMEOUT_NS 4000000000ull   // 4 s: a wait this long is a protocol bug or a dead peer
+#define TB_SPIN_TIMEOUT_NS 300000000000ull   // default 300 s; set at run time with TUTEL_B200_SPIN_TIMEOUT_SEC
 #endif
+
+// Every spin-wait (mbarrier pipelines and cross-GPU flags alike: a GEMM whose producer waits for a late peer stalls its
+// MMA and epilogue warps on their mbarriers for just as long) is bounded by this run-time value.  It lives in constant
+// memory and is only read on the slow path, after a first poll has failed.  One copy per translation unit; the host
+// setters (set_spin_timeout_*) keep them in sync.
+static __constant__ unsigned long long tb_spin_timeout_ns = TB_SPIN_TIMEOUT_NS;
 
 namespace ptx {
 
@@ -83,7 +89,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = globaltimer_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > TB_SPIN_TIMEOUT_NS) {
+    if (globaltimer_ns() - t0 > tb_spin_timeout_ns) {
       printf("[tutel_b200] mbarrier wait timeout: block %d thread %d bar 0x%x parity %u\n", blockIdx.x,
              threadIdx.x, bar, parity);
       __trap();
@@ -138,7 +144,7 @@ __device__ __forceinline__ uint32_t wait_mailbox_sys(const unsigned long long* p
     __nanosleep(64);
     v = ld_acquire_sys_u64(p);
     if (static_cast<int32_t>(static_cast<uint32_t>(v >> 32) - epoch) >= 0) return static_cast<uint32_t>(v);
-    if (globaltimer_ns() - t0 > TB_SPIN_TIMEOUT_NS) {
+    if (globaltimer_ns() - t0 > tb_spin_timeout_ns) {
       printf("[tutel_b200] peer mailbox wait timeout: block %d mailbox %p have epoch %u want %u\n", blockIdx.x, p,
              static_cast<uint32_t>(v >> 32), epoch);
       __trap();
@@ -152,7 +158,7 @@ __device__ __forceinline__ void wait_flag_ge_sys(const uint32_t* p, uint32_t tar
   const uint64_t t0 = globaltimer_ns();
   while (static_cast<int32_t>(ld_acquire_sys(p) - target) < 0) {
     __nanosleep(64);
-    if (globaltimer_ns() - t0 > TB_SPIN_TIMEOUT_NS) {
+    if (globaltimer_ns() - t0 > tb_spin_timeout_ns) {
       printf("[tutel_b200] peer flag wait timeout: block %d thread %d flag %p have %u want %u\n", blockIdx.x,
              threadIdx.x, p, ld_relaxed_sys(p), target);
       __trap();

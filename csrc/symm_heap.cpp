@@ -157,6 +157,8 @@ int et_of(at::ScalarType t) {
     case at::kFloat: return tb::ET_F32;
     case at::kHalf: return tb::ET_F16;
     case at::kBFloat16: return tb::ET_BF16;
+    case at::kInt: return tb::ET_I32;
+    case at::kLong: return tb::ET_I64;
     default: TORCH_CHECK(false, "unsupported dtype for P2P reduce: ", t);
   }
 }
@@ -252,6 +254,34 @@ void register_symm_bindings(pybind11::module& m) {
     TB_CHECK_CUDA(tb::p2p_reduce_slice(out.data_ptr(), reinterpret_cast<const unsigned long long*>(peer_table),
                                        stage_off, slice_off_bytes, out.numel(), et_of(out.scalar_type()),
                                        static_cast<int>(rank), static_cast<int>(world), is_max, cur_stream()));
+  });
+  m.def("p2p_allreduce_oneshot", [](const at::Tensor& in, at::Tensor& out, int64_t peer_table, int64_t inbox_off,
+                                    int64_t slot_bytes, int64_t flag_off, int64_t rank, int64_t world, int64_t epoch,
+                                    bool is_max) {
+    TORCH_CHECK(in.is_cuda() && in.is_contiguous() && out.is_cuda() && out.is_contiguous() &&
+                in.scalar_type() == out.scalar_type() && in.numel() == out.numel());
+    const c10::cuda::CUDAGuard guard(in.device());
+    TB_CHECK_CUDA(tb::p2p_allreduce_oneshot(in.data_ptr(), out.data_ptr(), reinterpret_cast<const unsigned long long*>(peer_table),
+                                            inbox_off, slot_bytes, flag_off, in.numel(), et_of(in.scalar_type()),
+                                            static_cast<int>(rank), static_cast<int>(world), static_cast<uint32_t>(epoch),
+                                            is_max, cur_stream()));
+  });
+  m.def("p2p_oneshot_max_blocks", []() { return static_cast<int64_t>(tb::kOneShotMaxBlocks); });
+  // [rows, cols, width] -> [cols, rows, width] record transpose (2-D hierarchical all-to-all phases)
+  m.def("p2p_stride_copy", [](const at::Tensor& src, at::Tensor& dst, int64_t rows, int64_t cols) {
+    TORCH_CHECK(src.is_cuda() && src.is_contiguous() && dst.is_cuda() && dst.is_contiguous() &&
+                src.numel() == dst.numel() && src.scalar_type() == dst.scalar_type() && rows * cols > 0 &&
+                src.numel() % (rows * cols) == 0);
+    const c10::cuda::CUDAGuard guard(src.device());
+    const int64_t width = src.numel() / (rows * cols) * static_cast<int64_t>(src.element_size());
+    TB_CHECK_CUDA(tb::p2p_stride_copy(src.data_ptr(), dst.data_ptr(), static_cast<int>(rows), static_cast<int>(cols), width,
+                                      cur_stream()));
+  });
+  m.def("set_spin_timeout", [](double seconds) {
+    const unsigned long long ns = static_cast<unsigned long long>(seconds * 1e9);
+    TB_CHECK_CUDA(tb::set_spin_timeout_moe(ns));
+    TB_CHECK_CUDA(tb::set_spin_timeout_p2p(ns));
+    TB_CHECK_CUDA(tb::set_spin_timeout_gemm(ns));
   });
   m.def("p2p_barrier", [](int64_t peer_table, int64_t bar_off, int64_t rank, int64_t world, int64_t epoch) {
     TB_CHECK_CUDA(tb::p2p_barrier(reinterpret_cast<const unsigned long long*>(peer_table), bar_off,

@@ -102,16 +102,6 @@ def test_encode_decode_gate_grad_match_cpu(C, dtype, M):
     assert torch.allclose(gg.cpu(), ref, atol=tol * M ** 0.5, rtol=tol)
 
 
-def test_fused_gate_forward(C):
-    torch.manual_seed(4)
-    logits = torch.randn(777, 130, device='cuda')
-    scores, idx, top, me, ce = C.gate_topk_forward(logits, 4)
-    ref = torch.softmax(logits, dim=1)
-    tv, ti = torch.topk(ref, 4, dim=1)
-    assert torch.allclose(scores, ref, atol=1e-6) and torch.equal(idx.t().long(), ti) and torch.allclose(top.t(), tv, atol=1e-6)
-    assert torch.allclose(me.sum(0), ref.sum(0), rtol=1e-4) and torch.equal(ce.sum(0).long(), torch.bincount(ti[:, 0], minlength=130))
-
-
 def test_nvrtc_jit_kernel():
     from tutel_b200 import jit
     fn = jit.create_cuda_kernel(r'''
@@ -326,22 +316,3 @@ def test_llama_ffn_expert_fused_glu_matches_autograd(act, fp8):
         assert max(errs) < 0.02, errs
 
 
-@pytest.mark.skipif(__import__('os').environ.get('TUTEL_B200_TEST_EXPERIMENTAL', '0') != '1',
-                    reason='opt-in: fused gating path (TUTEL_B200_FUSED_GATE) is not enabled by default yet')
-@pytest.mark.parametrize('E,k', [(8, 2), (130, 4)])
-def test_fused_gate_autograd_cuda_matches_torch_branch(E, k):
-    """CUDA gate_topk_forward/backward kernels vs the pure-torch branch of ops/gating.FusedTopKGate (CPU-verified)."""
-    from tutel_b200.ops.gating import fused_topk_gate
-    torch.manual_seed(6)
-    S = 777
-    base = torch.randn(S, E)
-    wg = torch.randn(k, S)
-    outs = []
-    for dev in ('cpu', 'cuda'):
-        logits = base.to(dev).requires_grad_(True)
-        idx, gates, l_aux, top1 = fused_topk_gate(logits, k, True, True)
-        ((gates * wg.to(dev)).sum() + 2.0 * l_aux).backward()
-        outs.append((idx.cpu(), gates.detach().cpu(), l_aux.detach().cpu(), logits.grad.cpu()))
-    assert torch.equal(outs[0][0], outs[1][0])
-    for a, b in zip(outs[0][1:], outs[1][1:]):
-        assert torch.allclose(a, b, atol=2e-6, rtol=1e-4)

@@ -55,6 +55,9 @@ def test_activation_classification():
     assert classify_activation(lambda x: F.silu(x)) == 'silu' and classify_activation(torch.tanh) is None
     drop = torch.nn.Dropout(0.5)
     assert classify_activation(lambda x: drop(F.relu(x))) is None      # stochastic -> never fused
+    # clamped variants agree with ReLU on small inputs only: they must not be taken for ReLU
+    assert classify_activation(F.relu6) is None and classify_activation(lambda x: torch.clamp(x, 0, 5)) is None
+    assert classify_activation(lambda x: F.hardtanh(x, 0.0, 1000.0)) is None
 
 
 def test_launcher_builds_torchrun_command(monkeypatch):
@@ -75,6 +78,12 @@ def test_launcher_builds_torchrun_command(monkeypatch):
     monkeypatch.setenv('LOCAL_RANK', '3')
     execl.main()
     assert seen['env']['CUDA_VISIBLE_DEVICES'] == '3' and seen['cmd'][-2:] == ['-m', 'my.prog']
+    assert seen['cmd'][0] == sys.executable
+    # reference-style `launcher.run python3 train.py ..`: the command is exec'd as given, no interpreter is prepended
+    monkeypatch.setenv('NUMA_TYPE', '0')
+    monkeypatch.setattr(sys, 'argv', ['execl', 'python3', 'train.py', '--x'])
+    execl.main()
+    assert seen['cmd'] == ['python3', 'train.py', '--x']
 
 
 def test_fairseq_style_conversion(monkeypatch):

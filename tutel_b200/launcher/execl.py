@@ -18,7 +18,9 @@ def main():
     local_size = int(env.get('LOCAL_SIZE', 1))
     if int(env.get('TUTEL_CUDA_SANDBOX', 0)) == 2:
         env['CUDA_VISIBLE_DEVICES'] = str(local_rank)
-    cmd = [sys.executable] + argv
+    # `-m module args..` runs a module with this interpreter; anything else is a complete command line that is exec'd
+    # as given (`python3 train.py ..`, a shell script, ..) - the reference's contract (tutel/launcher/execl.py:36-41)
+    cmd = [sys.executable, '-m'] + argv[1:] if argv[0] == '-m' else list(argv)
     numactl = shutil.which('numactl')
     if numactl and int(env.get('NUMA_TYPE', '1')) > 0:
         try:

@@ -26,8 +26,8 @@ from torch import Tensor
 from torch.nn import ModuleList
 
 from ..ops.dispatch import fast_decode, fast_encode
-from ..ops.gating import fused_gate_enabled, fused_topk_gate
-from ..ops.routing import extract_critical, get_dispatch_count
+from ..ops.gating import fused_gate_mode, fused_gate_route_available, fused_topk_gate
+from ..ops.routing import extract_critical, fused_extract_critical, get_dispatch_count
 from ..parallel import communicate as C
 from ..parallel.overlap import a2a_ffn_overlap_forward
 from ..utils.trace import stage
@@ -251,10 +251,21 @@ class MOELayer(torch.nn.Module):
             logits_w_noise = logits + gctx.gate_noise * torch.randn_like(logits) / self.num_global_experts
         else:
             logits_w_noise = logits
-        fused_gate = None
-        if self.is_gshard_loss and fused_gate_enabled() and logits_w_noise.dim() == 2:
-            # one kernel forward / one backward for softmax + top-k + gate normalisation + GShard loss (ops/gating.py)
-            k_eff = min(top_k, self.num_global_experts)
+        mega = max(megablocks_size, 1)
+        alignment = (self.sharded_count * a2a_ffn_overlap_degree + mega - 1) // mega * mega
+        if alignment > 256:
+            alignment = (alignment + 127) // 128 * 128
+        fused_gate, gate_mode = None, fused_gate_mode()
+        k_eff = min(top_k, self.num_global_experts)
+        cuda_fused = (self.is_gshard_loss and gate_mode != 'off' and not self.batch_prioritized_routing and
+                      fused_gate_route_available(logits_w_noise, k_eff))
+        if cuda_fused or (self.is_gshard_loss and gate_mode == 'force' and logits_w_noise.dim() == 2):
+            if cuda_fused:
+                # CUDA: gate + routing in two launches, gate backward in one (ops/gating.py, csrc/gate_route.cu)
+                crit, l_aux = fused_extract_critical(logits_w_noise, top_k, capacity_factor or gctx.capacity_factor,
+                                                     self.normalize_gate, alignment, self.group, inequivalent_tokens)
+                return logits.dtype, crit, l_aux
+            # same formulas, op by op (CPU, batch-prioritised routing): one autograd node for softmax + top-k + loss
             fused_gate = fused_topk_gate(logits_w_noise, k_eff, self.normalize_gate, True)
             scores = logits_w_noise                # only its shape is read below
         else:
@@ -265,10 +276,6 @@ class MOELayer(torch.nn.Module):
             def loss_fn(gates, topk_ids):
                 return losses.load_importance_loss(F.softmax(logits, dim=1), logits_w_noise.gather(index=topk_ids, dim=1),
                                                    self.num_global_experts, gctx.gate_noise)
-        mega = max(megablocks_size, 1)
-        alignment = (self.sharded_count * a2a_ffn_overlap_degree + mega - 1) // mega * mega
-        if alignment > 256:
-            alignment = (alignment + 127) // 128 * 128
         crit, l_aux = extract_critical(scores, top_k=top_k, loss_fn=loss_fn,
                                        capacity_factor=capacity_factor or gctx.capacity_factor,
                                        batch_prioritized_routing=self.batch_prioritized_routing,

@@ -70,6 +70,18 @@ def raw_gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool
     return out
 
 
+def column_sums(t: torch.Tensor) -> torch.Tensor:
+    """``[G, T, N] -> [G, N]`` sums over the rows of every group (bias gradients) in t's dtype with fp32 accumulation:
+    a bandwidth-bound kernel (csrc/gate_route.cu) instead of torch's strided reduction + cast."""
+    if t.is_cuda and t.dim() == 3 and t.dtype in (torch.float32, torch.float16, torch.bfloat16) and backend.has_cuda_ext():
+        es = t.element_size()
+        if (t.stride(2) == 1 and t.data_ptr() % 16 == 0 and (t.stride(1) * es) % 16 == 0 and (t.stride(0) * es) % 16 == 0 and
+                (t.size(2) * es) % 16 == 0):
+            backend.count_launch()
+            return backend.require_ext().grouped_colsum(t)
+    return t.sum(dim=1, dtype=torch.float32).to(t.dtype)
+
+
 def _aligned(*dims: int) -> bool:
     return all(d % 8 == 0 for d in dims)
 
@@ -111,7 +123,7 @@ class GroupedLinear(torch.autograd.Function):
             else:    # dW[N,K] = dy^T[N,T] @ x[T,K]
                 dw = raw_gemm(dy, x, a_mn=True, b_mn=True)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy.sum(dim=1, dtype=torch.float32).to(dy.dtype)
+            db = column_sums(dy)
         return dx, dw, db, None, None, None
 
 
@@ -165,7 +177,7 @@ class FusedReluFFN(torch.autograd.Function):
             dh = _zero_tail(dh, rc)
             act = _zero_tail(act, rc)
         dw2 = raw_gemm(act, dy, a_mn=True, b_mn=True) if ctx.needs_input_grad[3] else None      # [H,Mout] = act^T @ dy
-        db2 = dy.sum(dim=1, dtype=torch.float32).to(dy.dtype) if ctx.has_b2 and ctx.needs_input_grad[4] else None
+        db2 = column_sums(dy) if ctx.has_b2 and ctx.needs_input_grad[4] else None
         dx = raw_gemm(dh, w1, b_mn=True, row_counts=rc) if ctx.needs_input_grad[0] else None    # [T,M] = dh @ W1
         if dx is not None and rc is not None:
             dx = _zero_tail(dx, rc)
@@ -196,7 +208,10 @@ def classify_activation(fn) -> Optional[str]:
     if cached is not None:
         return cached or None
     if _PROBE is None:
-        _PROBE = torch.linspace(-4.0, 4.0, 257)
+        # dense around zero plus magnitudes up to 3e4 (fp16 range): clamped look-alikes (relu6, hardtanh, clamp(0, c)) differ
+        # from ReLU only on large inputs and must not be classified as ReLU
+        big = torch.logspace(0.7, 4.5, 64)
+        _PROBE = torch.cat([torch.linspace(-4.0, 4.0, 257), big, -big])
     kind = ''
     try:
         with torch.no_grad():

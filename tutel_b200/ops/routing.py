@@ -104,30 +104,54 @@ def extract_critical(scores: torch.Tensor, top_k: int, loss_fn=losses.gshard_los
         denom = torch.clamp(gates_ks.sum(dim=0, keepdim=True), min=torch.finfo(gates_ks.dtype).eps)
         gates_ks = gates_ks / denom
 
-    if inequivalent_tokens:
-        num_samples = torch.tensor(scores.size(0), device=scores.device)
-        num_samples = int(simple_all_reduce(num_samples, group=group, op=torch.distributed.ReduceOp.MAX))
-    else:
-        num_samples = int(scores.size(0))
+    num_samples = _num_samples(int(scores.size(0)), scores.device, group, inequivalent_tokens)
+    capacity = _capacity(num_samples, num_global_experts, top_k, top_k_original, capacity_factor, counts, group, alignment)
 
+    return CriticalData(num_global_experts, idx_ks, loc_ks, gates_ks, capacity, counts), l_loss
+
+
+def _num_samples(local: int, device, group, inequivalent_tokens: bool) -> int:
+    if not inequivalent_tokens:
+        return local
+    t = torch.tensor(local, device=device)
+    return int(simple_all_reduce(t, group=group, op=torch.distributed.ReduceOp.MAX))
+
+
+def _capacity(num_samples, num_global_experts, top_k, top_k_original, capacity_factor, counts, group, alignment) -> int:
+    """Slots per expert and source rank (tutel/impls/fast_dispatch.py:182-200): a positive factor is a static multiple
+    of the even share, zero means "as large as the fullest expert anywhere" (dropless), a negative factor caps that."""
     samples_per_expert = (num_samples + num_global_experts - 1) // num_global_experts
     if capacity_factor > 0:
         capacity = top_k * int(capacity_factor * samples_per_expert)
     else:
-        capacity = counts.max()
-        capacity = int(simple_all_reduce(capacity, group=group, op=torch.distributed.ReduceOp.MAX))
+        capacity = int(simple_all_reduce(counts.max(), group=group, op=torch.distributed.ReduceOp.MAX))
         if capacity_factor < 0:
             capacity = min(capacity, top_k * int(-capacity_factor * samples_per_expert))
-
     remainder = capacity % alignment
     if remainder > 0:
         capacity = capacity + alignment - remainder
-
     if logging.getLogger().isEnabledFor(logging.INFO) and get_world_rank(group) == 0:
         logging.info('Capacity = %s, real-time capacity-factor for top-%s = %s', capacity, top_k_original,
                      capacity / max(top_k * samples_per_expert, 1))
+    return capacity
 
-    return CriticalData(num_global_experts, idx_ks, loc_ks, gates_ks, capacity, counts), l_loss
+
+def fused_extract_critical(logits: torch.Tensor, top_k: int, capacity_factor: float = 1.0, normalize_gate: bool = True,
+                           alignment: int = 1, group=None, inequivalent_tokens: bool = False):
+    """CUDA fast path of :func:`extract_critical` for GShard-loss top-k gates: softmax, top-k, gate normalisation, the
+    auxiliary loss, queue locations, counts and the inverse slot map come out of TWO kernel launches
+    (:func:`tutel_b200.ops.gating.fused_gate_route`); with a positive capacity factor nothing touches the host."""
+    from .gating import fused_gate_route
+    E = int(logits.size(1))
+    top_k_original, top_k = top_k, min(top_k, E)
+    num_samples = _num_samples(int(logits.size(0)), logits.device, group, inequivalent_tokens)
+    static_cap = _capacity(num_samples, E, top_k, top_k_original, capacity_factor, None, group, alignment) if capacity_factor > 0 else 0
+    idx, loc, gates, l_aux, counts, _top1, slot = fused_gate_route(logits, top_k, normalize_gate, static_cap)
+    capacity = static_cap if capacity_factor > 0 else \
+        _capacity(num_samples, E, top_k, top_k_original, capacity_factor, counts, group, alignment)
+    crit = CriticalData(E, idx, loc, gates, capacity, counts)
+    crit._slot_src = slot
+    return crit, l_aux
 
 
 def get_dispatch_count(critical_data):

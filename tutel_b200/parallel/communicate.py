@@ -181,10 +181,11 @@ def _p2p(group, tensor: torch.Tensor):
 def simple_all_reduce(input: torch.Tensor, group=None, op=dist.ReduceOp.SUM, inplace: bool = False):
     if get_world_size(group) == 1:
         return input
+    t = _p2p(group, input)
+    if t is not None and t.supports_reduce(input, op):
+        # one kernel, out of place unless asked otherwise: no defensive clone of the input is needed
+        return t.all_reduce_(input, op) if inplace else t.all_reduce(input.contiguous(), op)
     output = input if inplace else input.clone(memory_format=torch.contiguous_format)
-    t = _p2p(group, output)
-    if t is not None and t.supports_reduce(output, op):
-        return t.all_reduce_(output, op)
     dist.all_reduce(output, op=op, group=group)
     return output
 
@@ -350,15 +351,29 @@ def _raw_all_to_all(packed: torch.Tensor, group, use_2dh: bool) -> torch.Tensor:
             logging.info('use_2dh: single NVLink domain detected, using the flat peer-to-peer all-to-all')
             _WARNED_2DH[0] = True
         return simple_all_to_all(packed, group)
-    # 2DH: (1) intra-node exchange groups traffic per destination-local-rank, (2) inter-node exchange delivers it.
+    # 2DH: (1) intra-node exchange groups traffic per destination-local-rank, (2) inter-node exchange delivers it; the
+    # re-ordering between the phases is a block transpose of whole records (native stride-copy kernel on CUDA).
     env = create_groups_from_world(-ngpus)
     intra, inter = env.model_group, env.data_group
     rest = list(packed.shape[1:])
-    x = packed.reshape([nnodes, ngpus] + rest).transpose(0, 1).contiguous()          # [dst_local, dst_node, ...]
+    x = _block_transpose(packed.reshape([nnodes, ngpus] + rest), nnodes, ngpus)      # [dst_local, dst_node, ...]
     x = simple_all_to_all(x, intra)                                                   # [src_local, dst_node, ...]
-    x = x.reshape([ngpus, nnodes] + rest).transpose(0, 1).contiguous()                # [dst_node, src_local, ...]
+    x = _block_transpose(x.reshape([ngpus, nnodes] + rest), ngpus, nnodes)            # [dst_node, src_local, ...]
     x = simple_all_to_all(x, inter)                                                   # [src_node, src_local, ...]
     return x.reshape([world] + rest)
+
+
+def _block_transpose(x: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    """``[rows, cols, ...] -> [cols, rows, ...]`` as a contiguous tensor (one launch of the stride-copy kernel on CUDA)."""
+    if x.is_cuda and x.numel() > 0:
+        from ..ops import backend
+        if backend.has_cuda_ext():
+            src = x.contiguous()
+            dst = torch.empty([cols, rows] + list(x.shape[2:]), dtype=x.dtype, device=x.device)
+            backend.count_launch()
+            backend.require_ext().p2p_stride_copy(src, dst, rows, cols)
+            return dst
+    return x.transpose(0, 1).contiguous()
 
 
 class _AllToAll(torch.autograd.Function):

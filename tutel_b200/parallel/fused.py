@@ -96,8 +96,9 @@ class FusedEngine:
         free = [s for s in ring if not s.busy]
         if len(ring) < _MIN_RING or not free:
             if len(ring) >= _MAX_RING and not free:
-                # forwards whose backward never ran keep their set reserved; recycle the oldest one
-                return self._take(min(ring, key=lambda s: s.last_used), hold)
+                # every set is still referenced by a forward whose backward has not run (deep micro-batching, weight
+                # sharing): its saved rows must not be overwritten, so this call takes the generic all-to-all path
+                return None
             if not self.t.can_alloc(_BufferSet.bytes_needed(self, C)):
                 return None if not free else self._take(min(free, key=lambda s: s.last_used), hold)
             ring.append(_BufferSet(self, len(ring), C))
@@ -328,8 +329,7 @@ class _FusedMoE(torch.autograd.Function):
         dw2 = G.raw_gemm(act_e, dy_recv.view(El, W * C, Mo), a_mn=True, b_mn=True) if ctx.needs_input_grad[9] else None
         dw1 = G.raw_gemm(dh_e, x_recv.view(El, W * C, M), a_mn=True, b_mn=True) if ctx.needs_input_grad[7] else None
         db1 = db1_acc.to(dh.dtype) if want_db1 else None
-        db2 = (dy_recv.view(El, W * C, Mo).sum(dim=1, dtype=torch.float32).to(dh.dtype)
-               if ctx.has_b2 and ctx.needs_input_grad[10] else None)
+        db2 = G.column_sums(dy_recv.view(El, W * C, Mo)) if ctx.has_b2 and ctx.needs_input_grad[10] else None
 
         # (g) combine the input gradients (encode.bwd == decode of the gradient buffer)
         dx = None

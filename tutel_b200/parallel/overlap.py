@@ -17,8 +17,6 @@ from __future__ import annotations
 from typing import Any, Callable, List
 
 import torch
-import torch.distributed as dist
-
 from . import communicate as C
 
 MAX_OVERLAP_DEGREE = 32
@@ -42,63 +40,65 @@ def _comm_stream(device) -> torch.cuda.Stream:
     return _COMM_STREAMS[key]
 
 
-def _start_exchange(packed: torch.Tensor, group, pending: _Pending) -> None:
-    """Start an all-to-all along dim 0 of ``packed`` without blocking the current stream."""
+def _start_exchange(packed: torch.Tensor, group, pending: _Pending, use_2dh: bool = False) -> None:
+    """Start an all-to-all along dim 0 of ``packed`` (flat or 2-D hierarchical) without blocking the current stream."""
     packed = packed.contiguous()
+    if not packed.is_cuda:
+        pending.out, pending.wait = C._raw_all_to_all(packed, group, use_2dh), (lambda: None)
+        return
+    cur = torch.cuda.current_stream()
+    side = _comm_stream(packed.device)
+    side.wait_stream(cur)
     t = C._p2p(group, packed)
-    if t is not None:
-        cur = torch.cuda.current_stream()
-        side = _comm_stream(packed.device)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            out = t.all_to_all(packed)
-            ev = torch.cuda.Event()
-            ev.record(side)
-        packed.record_stream(side)
-        # `out` lives in the transport's arena pool: its block is only re-used by a later collective, which is ordered
-        # after everything queued on the consumer stream (wait_stream above)
-        pending.out, pending.wait = out, (lambda: torch.cuda.current_stream().wait_event(ev))
-    elif packed.is_cuda:
-        out = torch.empty_like(packed)
-        work = dist.all_to_all_single(out, packed, group=group, async_op=True)
-        pending.out, pending.wait = out, work.wait
-    else:
-        pending.out, pending.wait = C.simple_all_to_all(packed, group), (lambda: None)
+    with torch.cuda.stream(side):
+        if t is not None and not use_2dh:
+            # own counter slot: a main-stream P2P collective inside the expert function must not share epochs / mailboxes
+            # with the exchanges that are in flight on this stream
+            out = t.all_to_all(packed, slot=t.side_slot())
+        else:
+            out = C._raw_all_to_all(packed, group, use_2dh)      # NCCL, or the two phases of the hierarchical exchange
+        ev = torch.cuda.Event()
+        ev.record(side)
+    packed.record_stream(side)
+    out.record_stream(cur)
+    # a result living in the transport's arena pool is only re-used by a later collective, which is ordered after
+    # everything queued on the consumer stream (wait_stream above)
+    pending.out, pending.wait = out, (lambda: torch.cuda.current_stream().wait_event(ev))
 
 
 class _Begin(torch.autograd.Function):
     @staticmethod
-    def forward(ctx: Any, packed: torch.Tensor, group, fwd: _Pending, bwd: _Pending):
+    def forward(ctx: Any, packed: torch.Tensor, group, fwd: _Pending, bwd: _Pending, use_2dh: bool):
         ctx.bwd = bwd
-        _start_exchange(packed, group, fwd)
+        _start_exchange(packed, group, fwd, use_2dh)
         return fwd.out
 
     @staticmethod
     def backward(ctx: Any, grad: torch.Tensor):
         # the mirrored exchange was started by _End.backward; `grad` is its output buffer
         ctx.bwd.wait()
-        return ctx.bwd.out, None, None, None
+        return ctx.bwd.out, None, None, None, None
 
 
 class _End(torch.autograd.Function):
     @staticmethod
-    def forward(ctx: Any, raw: torch.Tensor, group, fwd: _Pending, bwd: _Pending):
-        ctx.group, ctx.bwd = group, bwd
+    def forward(ctx: Any, raw: torch.Tensor, group, fwd: _Pending, bwd: _Pending, use_2dh: bool):
+        ctx.group, ctx.bwd, ctx.use_2dh = group, bwd, use_2dh
         fwd.wait()
         return raw.view_as(raw)
 
     @staticmethod
     def backward(ctx: Any, grad: torch.Tensor):
-        _start_exchange(grad, ctx.group, ctx.bwd)
-        return ctx.bwd.out, None, None, None
+        _start_exchange(grad, ctx.group, ctx.bwd, ctx.use_2dh)
+        return ctx.bwd.out, None, None, None, None
 
 
-def _async_all_to_all(x: torch.Tensor, input_dim: int, output_dim: int, group) -> Callable[[], torch.Tensor]:
+def _async_all_to_all(x: torch.Tensor, input_dim: int, output_dim: int, group, use_2dh: bool = False) -> Callable[[], torch.Tensor]:
     """Start ``all_to_all(x, input_dim, output_dim)``; the returned callable finishes it (autograd-aware)."""
     world = C.get_world_size(group)
     fwd, bwd = _Pending(), _Pending()
-    raw = _Begin.apply(C._a2a_pack(x, output_dim, world), group, fwd, bwd)
-    return lambda: C._a2a_unpack(_End.apply(raw, group, fwd, bwd), input_dim)
+    raw = _Begin.apply(C._a2a_pack(x, output_dim, world), group, fwd, bwd, use_2dh)
+    return lambda: C._a2a_unpack(_End.apply(raw, group, fwd, bwd, use_2dh), input_dim)
 
 
 def a2a_ffn_overlap_forward(input: torch.Tensor, expert_fn: Callable[[torch.Tensor], torch.Tensor],
@@ -110,14 +110,11 @@ def a2a_ffn_overlap_forward(input: torch.Tensor, expert_fn: Callable[[torch.Tens
     if C.get_world_size(group) == 1:
         return expert_fn(input)
     chunks = input.split(input.shape[1] // d, dim=1)
-    if use_2dh:
-        # hierarchical exchange has no asynchronous form: keep the chunking (identical numerics), run in order
-        outs = [C.all_to_all(expert_fn(C.all_to_all(c, 1, 0, group=group, use_2dh=True)), 0, 1, group=group, use_2dh=True)
-                for c in chunks]
-        return torch.cat(outs, dim=1)
-    arrivals = [_async_all_to_all(c, 1, 0, group) for c in chunks]        # all dispatch exchanges are in flight
+    # (the hierarchical exchange pipelines the same way: both of its phases and the record transposes between them run on
+    # the communication stream - the reference's AllToAll2DAsync, tutel/custom/custom_kernel.cpp:656-738)
+    arrivals = [_async_all_to_all(c, 1, 0, group, use_2dh) for c in chunks]   # all dispatch exchanges are in flight
     returns: List[Callable[[], torch.Tensor]] = []
     for arrive in arrivals:
         y = expert_fn(arrive())                                           # waits only for its own chunk
-        returns.append(_async_all_to_all(y, 0, 1, group))                 # combine exchange overlaps the next chunk
+        returns.append(_async_all_to_all(y, 0, 1, group, use_2dh))        # combine exchange overlaps the next chunk
     return torch.cat([r() for r in returns], dim=1)

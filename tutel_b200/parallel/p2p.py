@@ -61,8 +61,6 @@ def _create(group) -> Optional['P2PTransport']:
     world = dist.get_world_size(group)
     if world <= 1 or world > _MAX_PEERS:
         return None
-    if not (group is None or group is dist.group.WORLD) and world != dist.get_world_size():
-        return None  # sub-groups keep using NCCL in this version
     if dist.get_backend(group) != 'nccl':
         return None
     # single NVLink domain check: same host, distinct devices, peer access possible
@@ -87,8 +85,16 @@ class P2PTransport:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.device = torch.cuda.current_device()
-        heap_mb = int(os.environ.get('TUTEL_B200_HEAP_MB', 12288))
-        stage_mb = int(os.environ.get('TUTEL_B200_STAGE_MB', 4096))
+        # The whole-world transport carries the fused MoE buffers (TUTEL_B200_HEAP_MB); sub-groups (model / data groups of
+        # `create_groups_from_world`, ZeRO sharers, the two phases of the hierarchical all-to-all) get their own, smaller
+        # arena, exchanged among the members only (TUTEL_B200_SUBHEAP_MB).
+        self.is_world = group is None or group is dist.group.WORLD or self.world == dist.get_world_size()
+        if self.is_world:
+            heap_mb = int(os.environ.get('TUTEL_B200_HEAP_MB', 8192))
+            stage_mb = int(os.environ.get('TUTEL_B200_STAGE_MB', 2048))
+        else:
+            heap_mb = int(os.environ.get('TUTEL_B200_SUBHEAP_MB', 1536))
+            stage_mb = int(os.environ.get('TUTEL_B200_SUBSTAGE_MB', 1024))
         self.heap_bytes = heap_mb << 20
         self.stage_off = _CTRL_BYTES
         self.stage_bytes = min(stage_mb << 20, self.heap_bytes // 2)
@@ -110,6 +116,12 @@ class P2PTransport:
         self._fault_calls = 0
         self._named: Dict[str, tuple] = {}
         self._next_slot = 2  # slot 0: generic push, slot 1: generic barrier/reduce
+        # one-shot all-reduce: inbox 2 (parity) x W slots of _ONESHOT_BYTES, one flag per (parity, source, block)
+        self._oneshot_inbox = self.alloc('__oneshot_inbox__', 2 * self.world * self._ONESHOT_BYTES)
+        self._oneshot_flags = self.ctrl_alloc('__oneshot_flags__', 2 * self.world * int(_C.p2p_oneshot_max_blocks()) * 4)
+        self._oneshot_epoch = 0
+        # bound of every spin-wait in the kernels (a rank may legitimately be late: data loading, checkpointing)
+        _C.set_spin_timeout(float(os.environ.get('TUTEL_B200_SPIN_TIMEOUT_SEC', 300)))
 
     # ---- fault injection (a dead peer must produce a diagnostic, not a hang) --------------------------
     def _parse_fault(self, spec: str):
@@ -209,7 +221,15 @@ class P2PTransport:
         # that every rank evaluates identically is against the bounce region
         return nbytes <= self.bounce_bytes
 
-    def all_to_all(self, x: torch.Tensor, copy: bool = True) -> torch.Tensor:
+    def side_slot(self) -> int:
+        """Counter slot (mailboxes / done counters / epoch sequence) reserved for collectives issued on a side stream
+        (parallel/overlap.py): kernels sharing a slot must be serialised on one stream, and main-stream collectives
+        (e.g. a `zero_gather` inside the expert function) may run while chunk exchanges are in flight."""
+        if getattr(self, '_side_slot', None) is None:
+            self._side_slot = self.new_counter_slot()
+        return self._side_slot
+
+    def all_to_all(self, x: torch.Tensor, copy: bool = True, slot: int = 0) -> torch.Tensor:
         nbytes = x.numel() * x.element_size()
         if not self.fits(nbytes) or nbytes % self.world:
             out = torch.empty_like(x)
@@ -217,7 +237,7 @@ class P2PTransport:
             return out
         chunk = nbytes // self.world
         return self.collective(x, [p * chunk for p in range(self.world)], [self.rank * chunk] * self.world,
-                               [chunk] * self.world, x.shape)
+                               [chunk] * self.world, x.shape, slot=slot)
 
     def all_gather(self, x: torch.Tensor) -> torch.Tensor:
         nbytes = x.numel() * x.element_size()
@@ -260,24 +280,50 @@ class P2PTransport:
         dst_off = [sum(matrix[s][d] for s in range(self.rank)) * es for d in range(self.world)]
         return self.collective(x, src_off, dst_off, [n * es for n in in_list], [sum(out_list)])
 
-    # ---- reductions: one-shot pull over NVLink for small tensors --------------------------------------------------
+    # ---- reductions ---------------------------------------------------------------------------------------------
+    # <= _ONESHOT_BYTES: ONE kernel (push to every peer's inbox + flags + local reduce in rank order, ~1 NVLink round trip);
+    # up to _REDUCE_MAX_BYTES: stage + barrier + pull-reduce + barrier.
+    _ONESHOT_BYTES = 256 << 10
     _REDUCE_MAX_BYTES = 4 << 20     # must stay below bounce_bytes
+    _ONESHOT_DTYPES = (torch.float32, torch.float16, torch.bfloat16, torch.int32, torch.int64)
+
+    def supports_oneshot(self, x: torch.Tensor, op) -> bool:
+        return (x.dtype in self._ONESHOT_DTYPES and op in (dist.ReduceOp.SUM, dist.ReduceOp.MAX) and
+                0 < x.numel() * x.element_size() <= self._ONESHOT_BYTES)
 
     def supports_reduce(self, x: torch.Tensor, op) -> bool:
+        if self.supports_oneshot(x, op):
+            return True
         return (x.dtype in (torch.float32, torch.float16, torch.bfloat16) and op in (dist.ReduceOp.SUM, dist.ReduceOp.MAX)
                 and x.numel() * x.element_size() <= self._REDUCE_MAX_BYTES and x.numel() > 0)
 
     def _stage(self, x: torch.Tensor) -> None:
         self.view(self.stage_off, [x.numel()], x.dtype).copy_(x.reshape(-1))
 
-    def all_reduce_(self, x: torch.Tensor, op=dist.ReduceOp.SUM) -> torch.Tensor:
+    def all_reduce(self, x: torch.Tensor, op=dist.ReduceOp.SUM, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Out-of-place all-reduce of a contiguous tensor (``out`` may be ``x`` itself)."""
+        if out is None:
+            out = torch.empty_like(x, memory_format=torch.contiguous_format)
+        if self.supports_oneshot(x, op):
+            if self._fault is not None and self._fault_fires():
+                return out.copy_(x) if out is not x else out     # fault injection: this rank skips the collective
+            src = x if x.is_contiguous() else x.contiguous()
+            self._oneshot_epoch += 1
+            backend.count_launch()
+            self._C.p2p_allreduce_oneshot(src, out, self.peer_table, self._oneshot_inbox, self._ONESHOT_BYTES,
+                                          self._oneshot_flags, self.rank, self.world, self._oneshot_epoch,
+                                          op == dist.ReduceOp.MAX)
+            return out
         self._stage(x)
         self.barrier()
-        out = x if x.is_contiguous() else torch.empty_like(x, memory_format=torch.contiguous_format)
         self._C.p2p_reduce_slice(out, self.peer_table, self.stage_off, 0, self.rank, self.world, op == dist.ReduceOp.MAX)
         self.barrier()
-        if out is not x:
-            x.copy_(out)
+        return out
+
+    def all_reduce_(self, x: torch.Tensor, op=dist.ReduceOp.SUM) -> torch.Tensor:
+        if x.is_contiguous():
+            return self.all_reduce(x, op, out=x)
+        x.copy_(self.all_reduce(x.contiguous(), op))
         return x
 
     def reduce_scatter(self, x: torch.Tensor, op=dist.ReduceOp.SUM) -> torch.Tensor:
