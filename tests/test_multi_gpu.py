@@ -15,10 +15,11 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-def _run(which, nproc):
+def _run(which, nproc, **extra_env):
+    env = dict(os.environ, TUTEL_B200_SPIN_TIMEOUT_SEC=os.environ.get('TUTEL_B200_SPIN_TIMEOUT_SEC', '30'), **extra_env)
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=%d' % nproc, '--master-addr',
            '127.0.0.1', '--master-port', str(next_port()), os.path.join(ROOT, 'tests', 'workers', 'p2p_worker.py'), which]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     assert p.returncode == 0 and 'WORKER_OK' in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
 
 
@@ -32,11 +33,31 @@ def test_fused_engine_matches_nccl_path():
     _run('fused', 2)
 
 
-@pytest.mark.skipif(_ngpu() < 2 or os.environ.get('TUTEL_B200_TEST_FAULT', '0') != '1',
-                    reason='opt-in (TUTEL_B200_TEST_FAULT=1): kills its worker processes through a device trap after ~4 s')
+@pytest.mark.skipif(_ngpu() < 2, reason='needs 2 GPUs')
+def test_fused_engine_matches_fp32_torch_oracle():
+    """Fused bf16 engine vs NCCL + torch.matmul in fp32 on identical weights (small shapes and the flagship shape)."""
+    _run('oracle', 2)
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason='needs 2 GPUs')
+def test_data_vs_model_parallel_and_overlap_equivalence_fp32():
+    _run('equiv', 2)
+
+
+@pytest.mark.skipif(_ngpu() < 4, reason='needs 4 GPUs')
+def test_subgroup_transports():
+    _run('sub', 4)
+
+
+@pytest.mark.skipif(_ngpu() < 4, reason='needs 4 GPUs')
+def test_hierarchical_all_to_all_native():
+    _run('2dh', 4, LOCAL_SIZE='2')
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason='needs 2 GPUs')
 def test_dead_peer_is_diagnosed_not_hung():
     """Fault injection: rank 1 skips one push collective; the other rank must report a peer-wait timeout and fail fast."""
-    env = dict(os.environ, TUTEL_B200_FAULT='skip_push:rank=1:call=2')
+    env = dict(os.environ, TUTEL_B200_FAULT='skip_push:rank=1:call=2', TUTEL_B200_SPIN_TIMEOUT_SEC='5')
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
            '--master-port', str(next_port()), os.path.join(ROOT, 'tests', 'workers', 'p2p_worker.py'), 'fault']
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)

@@ -46,6 +46,23 @@ def test_collectives(env):
     refm = zm.clone()
     dist.all_reduce(refm, op=dist.ReduceOp.MAX)
     check('all_reduce max', torch.equal(net.simple_all_reduce(zm, op=dist.ReduceOp.MAX), refm))
+    # one-shot all-reduce kernel: dtypes, ops, sizes around its 256 KiB limit, repeated calls (buffer parity)
+    for dt, n, op in ((torch.int32, 1, dist.ReduceOp.MAX), (torch.int64, 5, dist.ReduceOp.SUM), (torch.bfloat16, 32768, dist.ReduceOp.SUM),
+                      (torch.float16, 1001, dist.ReduceOp.MAX), (torch.float32, 65536, dist.ReduceOp.SUM),
+                      (torch.float32, 65537, dist.ReduceOp.SUM), (torch.float32, 3, dist.ReduceOp.SUM)):
+        for rep in range(3):
+            v = (torch.randn(n, device=dev) * 8).to(dt) if dt.is_floating_point else torch.randint(-99, 99, [n], device=dev, dtype=dt) + r
+            refv = v.clone()
+            dist.all_reduce(refv, op=op)
+            got = net.simple_all_reduce(v, op=op)
+            tol = 0 if not dt.is_floating_point or op == dist.ReduceOp.MAX else (1e-5 if dt == torch.float32 else 0.13)
+            check('all_reduce %s n=%d op=%s #%d' % (str(dt).split('.')[-1], n, 'max' if op == dist.ReduceOp.MAX else 'sum', rep),
+                  torch.allclose(got.float(), refv.float(), atol=tol * 8, rtol=tol) and got.data_ptr() != v.data_ptr())
+    w = torch.randn(4, 4096, device=dev).bfloat16()
+    outs = [torch.empty_like(w) for _ in range(W)]
+    mine = net.simple_all_reduce(w)
+    dist.all_gather(outs, mine)
+    check('all_reduce bit-identical on every rank', all(torch.equal(o, mine) for o in outs))
     # ragged
     counts = [(r + p) % 3 + 1 for p in range(W)]
     data = torch.arange(sum(counts), device=dev, dtype=torch.float32) + 100 * r
@@ -121,6 +138,136 @@ def test_fused_vs_nccl(env):
         check('fused==nccl llama_ffn nle=%d' % nle, ok)
 
 
+def test_subgroups(env):
+    """Model / data sub-groups get their own P2P transports (own arenas, exchanged among the members only)."""
+    W, r, dev = env.global_size, env.global_rank, env.local_device
+    g = net.create_groups_from_world(group_count=2)
+    for name, grp in (('model', g.model_group), ('data', g.data_group)):
+        n = dist.get_world_size(grp)
+        t = p2p.transport_for(grp)
+        check('sub-group transport (%s, %d ranks)' % (name, n), (t is not None) == (n > 1) and (t is None or t.world == n))
+        if n == 1:
+            continue
+        torch.manual_seed(300 + r)
+        x = torch.randn(n * 1000, device=dev)
+        ref = torch.empty_like(x)
+        dist.all_to_all_single(ref, x, group=grp)
+        check('%s-group all_to_all' % name, torch.equal(net.simple_all_to_all(x, group=grp), ref))
+        z = torch.randn(n * 6, 4, device=dev)
+        refz = z.clone()
+        dist.all_reduce(refz, group=grp)
+        check('%s-group all_reduce' % name, torch.allclose(net.simple_all_reduce(z, group=grp), refz, atol=1e-5))
+        y = torch.randn(5, 3, device=dev).bfloat16()
+        refy = torch.empty(n * 5, 3, device=dev, dtype=torch.bfloat16)
+        dist.all_gather_into_tensor(refy, y, group=grp)
+        check('%s-group all_gather' % name, torch.equal(net.simple_all_gather(y, group=grp), refy))
+
+
+def test_2dh(env):
+    """Hierarchical all-to-all (LOCAL_SIZE=2 simulates 2 nodes x 2 GPUs): stride-copy kernel + two sub-group phases."""
+    W, r, dev = env.global_size, env.global_rank, env.local_device
+    torch.manual_seed(400 + r)
+    x = torch.randn(W * 2, 6, 16, device=dev).bfloat16()
+    flat = net.all_to_all(x, 1, 0, use_2dh=False)
+    hier = net.all_to_all(x, 1, 0, use_2dh=True)
+    check('2dh == flat (1,0)', torch.equal(flat, hier))
+    check('2dh == flat (0,1)', torch.equal(net.all_to_all(flat, 0, 1, use_2dh=True), net.all_to_all(flat, 0, 1)))
+    os.environ['TUTEL_B200_FUSED'] = '0'
+    outs = []
+    for use_2dh, d in ((False, 1), (True, 1), (True, 2)):
+        torch.manual_seed(7)
+        layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2}, model_dim=64, use_2dh=use_2dh, a2a_ffn_overlap_degree=d,
+                              experts={'type': 'ffn', 'num_experts_per_device': 2, 'hidden_size_per_expert': 128,
+                                       'activation_fn': lambda t: F.relu(t)}, seeds=(1, r + 1, 1)).to(dev)
+        torch.manual_seed(50 + r)
+        xi = torch.randn(256, 64, device=dev, requires_grad=True)
+        y = layer(xi)
+        y.pow(2).mean().backward()
+        outs.append((y.detach(), xi.grad.clone(), layer.experts.batched_fc1_w.grad.clone()))
+    for tag, o in (('2dh d=1', outs[1]), ('2dh d=2 (async phases)', outs[2])):
+        check('layer %s == flat' % tag, all(torch.allclose(a, b, atol=1e-5, rtol=1e-4) for a, b in zip(o, outs[0])))
+    os.environ['TUTEL_B200_FUSED'] = '1'
+
+
+def _oracle_pair(env, nle, expert, tokens, model_dim, hidden, k=2, act=None):
+    """Fused bf16 engine vs a plain-PyTorch fp32 oracle (NCCL all-to-all + torch.matmul experts) on IDENTICAL,
+    bf16-representable weights / inputs and an fp32 gate (so both runs take the same routing decisions)."""
+    r, dev = env.global_rank, env.local_device
+    res = []
+    for fused in (True, False):
+        os.environ['TUTEL_B200_FUSED'] = '1' if fused else '0'
+        os.environ['TUTEL_B200_COMM'] = 'p2p' if fused else 'nccl'
+        torch.manual_seed(7)
+        layer = moe.moe_layer(gate_type={'type': 'top', 'k': k, 'fp32_gate': True, 'capacity_factor': 1.25}, model_dim=model_dim,
+                              experts={'type': expert, 'num_experts_per_device': nle, 'hidden_size_per_expert': hidden,
+                                       'activation_fn': act or (lambda t: F.relu(t))}, seeds=(1, r + 1, 1)).to(dev)
+        with torch.no_grad():
+            for prm in layer.parameters():
+                prm.copy_(prm.bfloat16().float())
+        if fused:
+            layer = layer.bfloat16()
+        torch.manual_seed(50 + r)
+        x = torch.randn(tokens, model_dim, device=dev).bfloat16()
+        xi = (x if fused else x.float()).clone().requires_grad_(True)
+        y = layer(xi)
+        dy = torch.randn(tokens, model_dim, device=dev, generator=torch.Generator(device=dev).manual_seed(9 + r)).bfloat16()
+        (y.float() * dy.float()).sum().backward()
+        ex = {n: p_.grad.float().clone() for n, p_ in layer.experts.named_parameters()}
+        res.append((y.float().detach(), xi.grad.float().clone(), ex, layer.gates[0].wg.weight.grad.float().clone()))
+        del layer
+    os.environ['TUTEL_B200_FUSED'], os.environ['TUTEL_B200_COMM'] = '1', 'p2p'
+
+    def rel(a, b):
+        return ((a - b).norm() / (b.norm() + 1e-12)).item()
+    errs = {'y': rel(res[0][0], res[1][0]), 'dx': rel(res[0][1], res[1][1]), 'dwg': rel(res[0][3], res[1][3])}
+    for n in res[0][2]:
+        errs['d' + n] = rel(res[0][2][n], res[1][2][n])
+    return errs
+
+
+def test_oracle(env):
+    big = os.environ.get('TUTEL_B200_TEST_FLAGSHIP', '1') == '1'
+    cases = [('ffn', 2, 512, 256, 512), ('llama_ffn', 1, 512, 256, 512)]
+    if big:
+        cases.append(('ffn', 8 // env.global_size if env.global_size <= 8 else 1, 8192, 4096, 14336))     # flagship shape
+    for expert, nle, tokens, M, H in cases:
+        errs = _oracle_pair(env, nle, expert, tokens, M, H, act=F.silu if expert == 'llama_ffn' else None)
+        worst = max(errs.values())
+        print('[rank %d] oracle %s M=%d H=%d rel errors: %s' % (env.global_rank, expert, M, H,
+                                                                 ' '.join('%s=%.4f' % kv for kv in sorted(errs.items()))), flush=True)
+        check('fused bf16 == fp32 torch oracle (%s, M=%d, H=%d)' % (expert, M, H), worst < 2e-2)
+
+
+def test_parallel_equivalence(env):
+    """fp32 on GPUs: a sharded expert gives the same losses under data and model parallelism, and for overlap 1 and 2
+    (the reference's GPU equivalence checks, tests/test_tutel.py:154-176)."""
+    W, r, dev = env.global_size, env.global_rank, env.local_device
+    runs = {}
+    for ptype, d in (('data', 1), ('model', 1), ('model', 2)):
+        torch.manual_seed(3)
+        layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2}, model_dim=128, parallel_type=ptype, a2a_ffn_overlap_degree=d,
+                              experts={'type': 'ffn', 'num_experts_per_device': -W, 'hidden_size_per_expert': 64 * W,
+                                       'activation_fn': lambda t: F.relu(t)}, seeds=(1, 1, 1)).to(dev)
+        opt = torch.optim.SGD(layer.parameters(), lr=1e-2)
+        torch.manual_seed(11)
+        x = torch.randn(256, 128, device=dev)
+        ls = []
+        for _ in range(4):
+            opt.zero_grad()
+            y = layer(x)
+            loss = y.pow(2).mean()
+            loss.backward()
+            if W > 1:
+                for prm in layer.gates.parameters():
+                    prm.grad = net.simple_all_reduce(prm.grad) / W
+            opt.step()
+            ls.append(float(loss))
+        runs[(ptype, d)] = ls
+    base = runs[('data', 1)]
+    for key, ls in runs.items():
+        check('sharded expert %s d=%d == data-parallel losses' % key, all(abs(a - b) <= 1e-5 * max(1, abs(b)) for a, b in zip(ls, base)))
+
+
 def main():
     env = system.init_data_model_parallel(backend='nccl')
     which = sys.argv[1] if len(sys.argv) > 1 else 'all'
@@ -128,6 +275,14 @@ def main():
         test_collectives(env)
     if which in ('all', 'fused'):
         test_fused_vs_nccl(env)
+    if which in ('all', 'oracle'):
+        test_oracle(env)
+    if which in ('all', 'equiv'):
+        test_parallel_equivalence(env)
+    if which in ('sub',) or (which == 'all' and env.global_size >= 4):
+        test_subgroups(env)
+    if which in ('2dh',) or (which == 'all' and env.global_size >= 4 and os.environ.get('LOCAL_SIZE') == '2'):
+        test_2dh(env)
     if which == 'fault':
         # launched with TUTEL_B200_FAULT=skip_push:rank=1:call=2 - the second all-to-all must end in a diagnosed timeout
         a = torch.ones(1 << 16, device=env.local_device)

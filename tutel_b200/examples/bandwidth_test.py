@@ -66,6 +66,7 @@ def main(argv=None):
             if args.compare_nccl and is_cuda and W > 1:
                 out = torch.empty_like(x)
                 cases.append(('nccl_all_to_all', lambda: dist.all_to_all_single(out, x)))
+                cases.append(('nccl_all_reduce', lambda: dist.all_reduce(out)))
             for name, fn in cases:
                 t = timed(fn, args.loop, dev, is_cuda)
                 algo = n * 4 * 1e-9 / t
