@@ -20,6 +20,7 @@ ap.add_argument('--tokens', type=int, default=32)
 ap.add_argument('--dim', type=int, default=2048)
 ap.add_argument('--dtype', default='float32')
 ap.add_argument('--iters', type=int, default=50)
+ap.add_argument('--graph', action='store_true', help='ours only: replay the forward as one CUDA graph (tutel_b200.utils.graph)')
 args = ap.parse_args()
 if args.impl == 'reference':
     sys.path.insert(0, os.path.join(ROOT, 'baseline', '_ref'))
@@ -39,18 +40,22 @@ layer = moe.moe_layer(gate_type={'type': 'top', 'k': 1, 'capacity_factor': 0.0},
                                'activation_fn': lambda x: F.relu(x)}, seeds=(1, 1, 1)).to(dev).eval()
 x = torch.randn(1, args.tokens, args.dim, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+call = (lambda t: layer(t, megablocks_size=args.megablocks_size)) if args.megablocks_size > 0 else (lambda t: layer(t))
+if args.graph and args.impl == 'ours':
+    from tutel_b200.utils.graph import GraphedForward
+    call = GraphedForward(call, x)
 times = []
 with torch.no_grad():
     for i in range(args.iters + 5):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        y = layer(x, megablocks_size=args.megablocks_size) if args.megablocks_size > 0 else layer(x)
+        y = call(x)
         e.record()
         torch.cuda.synchronize()
         if i >= 5:
             times.append(s.elapsed_time(e))
 times.sort()
-print(json.dumps({'impl': args.impl, 'config': 'dropless cf=0 top-1 E=%d tokens=%d dim=%d %s megablocks_size=%d' % (
-    args.experts, args.tokens, args.dim, args.dtype, args.megablocks_size), 'median_ms': times[len(times) // 2], 'min_ms': times[0],
+print(json.dumps({'impl': args.impl, 'config': 'dropless cf=0 top-1 E=%d tokens=%d dim=%d %s megablocks_size=%d%s' % (
+    args.experts, args.tokens, args.dim, args.dtype, args.megablocks_size, ' cuda-graph' if args.graph and args.impl == 'ours' else ''), 'median_ms': times[len(times) // 2], 'min_ms': times[0],
     'checksum': float(y.float().abs().sum())}))

@@ -4,6 +4,8 @@
 OUT=gpurun_out/r2c2
 mkdir -p $OUT
 export TUTEL_B200_SPIN_TIMEOUT_SEC=30
+timeout 600 python -m pytest tests/test_gpu_gate_route.py tests/test_gpu_kernels.py -x -q > $OUT/pytest_1gpu.log 2>&1; echo "pytest rc=$?"; tail -15 $OUT/pytest_1gpu.log
+for impl in ours reference; do timeout 200 python bench/dropless_bench.py --impl $impl --megablocks_size 1 > $OUT/dropless_$impl.json 2> $OUT/dropless_$impl.err; echo "dropless $impl rc=$?"; tail -1 $OUT/dropless_$impl.json; done
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1"
 for W in coll fused oracle equiv; do
   timeout 600 $T --master-port $((29700 + RANDOM % 200)) tests/workers/p2p_worker.py $W > $OUT/worker_$W.log 2>&1

@@ -188,9 +188,9 @@ def run_dispatch(c):
     idx_d, loc_d, gates_d, x_d = idx.cuda(), loc.cuda(), gates.cuda(), x.cuda()
     slot = _C.build_slot_map(idx_d, loc_d, E, C)
     out = torch.full((E * C, M), float('nan'), dtype=dt, device='cuda')
-    _C.encode_rows(x_d, gates_d, slot, out, k, E, C, 0, 0, 0, 0, 0, 0)
+    _C.encode_rows(x_d, gates_d, slot, out, k, E, C, 0, 0, 0, 0, 0, 0, None)
     out1 = torch.full((E * C, M), float('nan'), dtype=dt, device='cuda')
-    _C.encode_rows(x_d, None, slot, out1, k, E, C, 0, 0, 0, 3, 0, 0)
+    _C.encode_rows(x_d, None, slot, out1, k, E, C, 0, 0, 0, 3, 0, 0, None)
     tol = 1e-5 if dt == torch.float32 else 2e-2
     e1 = (out.float().cpu() - ref_enc).abs().max().item()
     e2 = (out1.float().cpu() - ref_enc1).abs().max().item()
@@ -206,7 +206,7 @@ def run_dispatch(c):
     # timing of the flagship shape
     if S >= 4096:
         ev = lambda: torch.cuda.Event(enable_timing=True)
-        for name, fn in (('encode_ms', lambda: _C.encode_rows(x_d, None, slot, out1, k, E, C, 0, 0, 0, 0, 0, 0)),
+        for name, fn in (('encode_ms', lambda: _C.encode_rows(x_d, None, slot, out1, k, E, C, 0, 0, 0, 0, 0, 0, None)),
                          ('decode_ms', lambda: _C.decode_rows(out1, gates_d, idx_d, loc_d, E, C, 0, 0)),
                          ('gate_grad_ms', lambda: _C.gate_grad(x_d, out1, idx_d, loc_d, E, C))):
             for _ in range(3):

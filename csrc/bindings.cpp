@@ -45,13 +45,14 @@ cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
 
 // a: [G, M, K] (a_mn=false) or [G, K, M] (a_mn=true); b: [Gb, N, K] (b_mn=false) or [Gb, K, N] (b_mn=true);
 // d: [G, M, N].  Innermost dims contiguous.  Pointer-table / flag arguments are raw device addresses (0 = off).
-void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, bool a_mn, bool b_mn, int64_t epilogue,
-          const c10::optional<at::Tensor>& bias, const c10::optional<at::Tensor>& aux,
-          const c10::optional<at::Tensor>& row_counts, double alpha, int64_t b_group_div, int64_t cta_group,
-          int64_t block_n, int64_t d_ptr_table, int64_t signal_ptr_table, int64_t wait_flags,
-          int64_t wait_rows_per_flag, int64_t wait_flags_per_group, int64_t wait_target, int64_t max_ctas,
-          int64_t group_rot, int64_t group_mod, const c10::optional<at::Tensor>& scale_a,
-          const c10::optional<at::Tensor>& scale_b, const c10::optional<at::Tensor>& colsum) {
+void gemm_ex(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, bool a_mn, bool b_mn, int64_t epilogue,
+             const c10::optional<at::Tensor>& bias, const c10::optional<at::Tensor>& aux,
+             const c10::optional<at::Tensor>& row_counts, double alpha, int64_t b_group_div, int64_t cta_group,
+             int64_t block_n, int64_t d_ptr_table, int64_t signal_ptr_table, int64_t wait_flags,
+             int64_t wait_rows_per_flag, int64_t wait_flags_per_group, int64_t wait_target, int64_t max_ctas,
+             int64_t group_rot, int64_t group_mod, const c10::optional<at::Tensor>& scale_a,
+             const c10::optional<at::Tensor>& scale_b, const c10::optional<at::Tensor>& colsum,
+             const c10::optional<at::Tensor>& d2, int64_t act) {
   TORCH_CHECK(a.is_cuda() && b.is_cuda() && d.is_cuda(), "tutel_b200.gemm: CUDA tensors required");
   TORCH_CHECK(a.dim() == 3 && b.dim() == 3 && d.dim() == 3, "tutel_b200.gemm: expected 3-D operands");
   TORCH_CHECK(a.stride(2) == 1 && b.stride(2) == 1 && d.stride(2) == 1, "tutel_b200.gemm: innermost dim must be contiguous");
@@ -122,9 +123,27 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, bool a_mn, bo
   p.wait_target = static_cast<uint32_t>(wait_target);
   p.group_rot = static_cast<int>(group_rot);
   p.group_mod = static_cast<int>(group_mod != 0 ? group_mod : 1);
+  if (d2.has_value() && d2->defined()) {
+    TORCH_CHECK(d2->is_cuda() && d2->scalar_type() == d.scalar_type() && d2->sizes() == d.sizes() && d2->strides() == d.strides(),
+                "tutel_b200.gemm: d2 must look like d");
+    p.d2 = d2->data_ptr();
+  }
+  if (act != 0) p.act = static_cast<int>(act);
   const char* why = nullptr;
   cudaError_t e = tb::gemm_sm100_launch(p, cur_stream(), &why);
   TORCH_CHECK(e == cudaSuccess, "tutel_b200.gemm launch failed: ", why ? why : cudaGetErrorString(e));
+}
+
+void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& d, bool a_mn, bool b_mn, int64_t epilogue,
+          const c10::optional<at::Tensor>& bias, const c10::optional<at::Tensor>& aux,
+          const c10::optional<at::Tensor>& row_counts, double alpha, int64_t b_group_div, int64_t cta_group,
+          int64_t block_n, int64_t d_ptr_table, int64_t signal_ptr_table, int64_t wait_flags,
+          int64_t wait_rows_per_flag, int64_t wait_flags_per_group, int64_t wait_target, int64_t max_ctas,
+          int64_t group_rot, int64_t group_mod, const c10::optional<at::Tensor>& scale_a,
+          const c10::optional<at::Tensor>& scale_b, const c10::optional<at::Tensor>& colsum) {
+  gemm_ex(a, b, d, a_mn, b_mn, epilogue, bias, aux, row_counts, alpha, b_group_div, cta_group, block_n, d_ptr_table,
+          signal_ptr_table, wait_flags, wait_rows_per_flag, wait_flags_per_group, wait_target, max_ctas, group_rot, group_mod,
+          scale_a, scale_b, colsum, c10::nullopt, 0);
 }
 
 std::vector<at::Tensor> route_locations(const at::Tensor& idx, int64_t E, int64_t C) {
@@ -161,7 +180,8 @@ at::Tensor build_slot_map(const at::Tensor& idx, const at::Tensor& loc, int64_t 
 // x [S, M]; gates float [k, S] or None; slot_src int [E*C]; out [E*C, M] (ignored rows live in dst_ptr_table).
 void encode_rows(const at::Tensor& x, const c10::optional<at::Tensor>& gates, const at::Tensor& slot_src,
                  at::Tensor& out, int64_t k, int64_t E, int64_t C, int64_t dst_ptr_table, int64_t signal_ptr_table,
-                 int64_t signal_rows, int64_t rot_chunks, int64_t signal_value, int64_t chunk_counters) {
+                 int64_t signal_rows, int64_t rot_chunks, int64_t signal_value, int64_t chunk_counters,
+                 const c10::optional<at::Tensor>& valid_rows) {
   TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous() && slot_src.is_cuda() && slot_src.is_contiguous());
   TORCH_CHECK(slot_src.scalar_type() == at::kInt && slot_src.numel() == E * C);
   const c10::cuda::CUDAGuard guard(x.device());
@@ -169,6 +189,11 @@ void encode_rows(const at::Tensor& x, const c10::optional<at::Tensor>& gates, co
   if (gates.has_value() && gates->defined()) {
     TORCH_CHECK(gates->is_cuda() && gates->scalar_type() == at::kFloat && gates->is_contiguous());
     g = gates->data_ptr();
+  }
+  const int* vr = nullptr;
+  if (valid_rows.has_value() && valid_rows->defined()) {
+    TORCH_CHECK(valid_rows->is_cuda() && valid_rows->scalar_type() == at::kInt && valid_rows->numel() >= E);
+    vr = valid_rows->data_ptr<int>();
   }
   if (dst_ptr_table == 0)
     TORCH_CHECK(out.is_cuda() && out.is_contiguous() && out.scalar_type() == x.scalar_type() &&
@@ -178,7 +203,43 @@ void encode_rows(const at::Tensor& x, const c10::optional<at::Tensor>& gates, co
                                 reinterpret_cast<const unsigned long long*>(signal_ptr_table),
                                 reinterpret_cast<unsigned int*>(chunk_counters), static_cast<int>(signal_rows), static_cast<int>(x.size(0)), static_cast<int>(E),
                                 static_cast<int>(k), static_cast<int>(C), static_cast<int>(x.size(1)), elem_type_of(x),
-                                static_cast<int>(rot_chunks), static_cast<int>(signal_value), cur_stream()));
+                                static_cast<int>(rot_chunks), static_cast<int>(signal_value), vr, cur_stream()));
+}
+
+// fp8 dispatch: x [S, M] (16-bit) -> e4m3 rows + fp32 row scales.  Local: returns [q [E*C, M], scale [E*C]]; remote push
+// (dst_ptr_table != 0): rows / scales / flags go through the pointer tables and nothing is returned.
+std::vector<at::Tensor> encode_rows_fp8(const at::Tensor& x, const c10::optional<at::Tensor>& gates, const at::Tensor& slot_src,
+                                        int64_t k, int64_t E, int64_t C, int64_t dst_ptr_table, int64_t scale_ptr_table,
+                                        int64_t signal_ptr_table, int64_t signal_rows, int64_t rot_chunks, int64_t signal_value,
+                                        int64_t chunk_counters) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous() && slot_src.is_cuda() && slot_src.is_contiguous());
+  TORCH_CHECK(slot_src.scalar_type() == at::kInt && slot_src.numel() == E * C && x.size(1) % 16 == 0 && x.element_size() == 2);
+  const c10::cuda::CUDAGuard guard(x.device());
+  const void* g = nullptr;
+  if (gates.has_value() && gates->defined()) {
+    TORCH_CHECK(gates->is_cuda() && gates->scalar_type() == at::kFloat && gates->is_contiguous());
+    g = gates->data_ptr();
+  }
+  std::vector<at::Tensor> out;
+  void* q = nullptr;
+  float* sc = nullptr;
+  if (dst_ptr_table == 0) {
+    out.push_back(at::empty({E * C, x.size(1)}, x.options().dtype(at::kFloat8_e4m3fn)));
+    out.push_back(at::empty({E * C}, x.options().dtype(at::kFloat)));
+    q = out[0].data_ptr();
+    sc = out[1].data_ptr<float>();
+  } else {
+    TORCH_CHECK(scale_ptr_table != 0, "encode_rows_fp8: a remote push needs scale_ptr_table");
+  }
+  TB_CHECK_CUDA(tb::encode_rows_fp8(x.data_ptr(), g, slot_src.data_ptr<int>(), q, sc,
+                                    reinterpret_cast<const unsigned long long*>(dst_ptr_table),
+                                    reinterpret_cast<const unsigned long long*>(scale_ptr_table),
+                                    reinterpret_cast<const unsigned long long*>(signal_ptr_table),
+                                    reinterpret_cast<unsigned int*>(chunk_counters), static_cast<int>(signal_rows),
+                                    static_cast<int>(x.size(0)), static_cast<int>(E), static_cast<int>(k), static_cast<int>(C),
+                                    static_cast<int>(x.size(1)), elem_type_of(x), static_cast<int>(rot_chunks),
+                                    static_cast<int>(signal_value), cur_stream()));
+  return out;
 }
 
 // buf [E*C, M]; gates float [k, S] or None; idx/loc int [k, S]; returns [S, M]
@@ -313,6 +374,17 @@ std::vector<at::Tensor> quantize_rows(const at::Tensor& x) {
   return {q, scale};
 }
 
+// q e4m3 [.., K], scale fp32 [..] -> 16-bit [.., K]
+at::Tensor dequant_rows(const at::Tensor& q, const at::Tensor& scale, at::ScalarType dtype) {
+  TORCH_CHECK(q.is_cuda() && q.is_contiguous() && q.scalar_type() == at::kFloat8_e4m3fn && scale.is_cuda() && scale.is_contiguous() &&
+              scale.scalar_type() == at::kFloat && q.dim() >= 2 && scale.numel() * q.size(-1) == q.numel());
+  const c10::cuda::CUDAGuard guard(q.device());
+  at::Tensor y = at::empty(q.sizes(), q.options().dtype(dtype));
+  TB_CHECK_CUDA(tb::dequant_rows_e4m3(q.data_ptr(), scale.data_ptr<float>(), y.data_ptr(), scale.numel(), static_cast<int>(q.size(-1)),
+                                      elem_type_of(y), cur_stream()));
+  return y;
+}
+
 // Gated-linear-unit GEMMs (SwiGLU / GeGLU / ReGLU experts; reference: tutel/experts/llama_ffn.py:38-41 runs three
 // cuBLAS GEMMs plus separate activation and multiply kernels).
 //   forward  (b2 given):  h = act(a*b) .* (a*b2)   [+ g = a*b -> d2, u = a*b2 -> d3 when given]   ONE launch
@@ -415,6 +487,32 @@ at::Tensor skinny_gemm(const at::Tensor& x, const at::Tensor& w, const c10::opti
   return y;
 }
 
+// x [G, R, K], w1 [G, H, K], w2 [G, H, N], biases [G, H] / [G, N] or None, counts int [G] or None -> fp32 [G, R, N]
+at::Tensor skinny_ffn(const at::Tensor& x, const at::Tensor& w1, const c10::optional<at::Tensor>& b1, const at::Tensor& w2,
+                      const c10::optional<at::Tensor>& b2, const c10::optional<at::Tensor>& counts, int64_t act) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 3 && w1.dim() == 3 && w2.dim() == 3 && x.is_contiguous() && w1.is_contiguous() && w2.is_contiguous());
+  TORCH_CHECK(x.scalar_type() == w1.scalar_type() && x.scalar_type() == w2.scalar_type() && x.size(0) == w1.size(0) && x.size(0) == w2.size(0));
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int G = static_cast<int>(x.size(0)), R = static_cast<int>(x.size(1)), K = static_cast<int>(x.size(2));
+  const int H = static_cast<int>(w1.size(1)), N = static_cast<int>(w2.size(2));
+  TORCH_CHECK(w1.size(2) == K && w2.size(1) == H, "skinny_ffn: weight shapes do not match");
+  at::Tensor y = at::zeros({G, R, N}, x.options().dtype(at::kFloat));
+  auto opt_ptr = [&](const c10::optional<at::Tensor>& t, int64_t n) -> const void* {
+    if (!t.has_value() || !t->defined()) return nullptr;
+    TORCH_CHECK(t->is_cuda() && t->is_contiguous() && t->scalar_type() == x.scalar_type() && t->numel() == n);
+    return t->data_ptr();
+  };
+  const int* c = nullptr;
+  if (counts.has_value() && counts->defined()) {
+    TORCH_CHECK(counts->is_cuda() && counts->scalar_type() == at::kInt && counts->numel() >= G);
+    c = counts->data_ptr<int>();
+  }
+  TB_CHECK_CUDA(tb::skinny_grouped_ffn(x.data_ptr(), w1.data_ptr(), opt_ptr(b1, static_cast<int64_t>(G) * H), w2.data_ptr(),
+                                       opt_ptr(b2, static_cast<int64_t>(G) * N), y.data_ptr<float>(), c, G, R, K, H, N,
+                                       static_cast<int>(act), elem_type_of(x), cur_stream()));
+  return y;
+}
+
 }  // namespace
 
 void register_symm_bindings(pybind11::module& m);  // symm_heap.cpp / p2p bindings
@@ -425,10 +523,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "tutel_b200 native runtime: sm_100a tcgen05 grouped GEMM, routing/dispatch kernels, symmetric heap, "
             "P2P collectives, NVRTC JIT";
   m.def("gemm", &gemm);
+  m.def("gemm_ex", &gemm_ex);
   m.def("gemm_glu", &gemm_glu);
   m.def("route_locations", &route_locations);
   m.def("build_slot_map", &build_slot_map);
   m.def("encode_rows", &encode_rows);
+  m.def("encode_rows_fp8", &encode_rows_fp8);
   m.def("decode_rows", &decode_rows);
   m.def("gate_grad", &gate_grad);
   m.def("gate_route_forward", &gate_route_forward);
@@ -436,7 +536,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("grouped_colsum", &grouped_colsum);
   m.def("cumsum_sub_one", &cumsum_sub_one);
   m.def("skinny_gemm", &skinny_gemm);
+  m.def("skinny_ffn", &skinny_ffn);
   m.def("quantize_rows", &quantize_rows);
+  m.def("dequant_rows", &dequant_rows);
   register_symm_bindings(m);
   register_cpu_bindings(m);
   register_jit_bindings(m);

@@ -260,7 +260,10 @@ __device__ __forceinline__ void glu_bwd_seg(const uint32_t* r, const float* g, f
 // its 228 KB shared memory, so ONE 128-thread x 64-register block of the dispatch kernel (encode_rows, which needs no
 // shared memory) always fits next to a GEMM CTA.  That is what makes the dispatch+GEMM fusion deadlock-free: a GEMM
 // whose producer spins on arrival flags can never starve the kernel that publishes them, whichever gets the SMs first.
-template <int CG, bool A_MN, bool B_MN, int BN, int ELT>
+// XACT selects the (rarely used) epilogues with transcendental activations - GELU / SiLU forward with the pre-activation
+// saved for training, and their gradient - in their own instantiations, so that their registers do not burden the
+// common ReLU / bias / GLU kernels.
+template <int CG, bool A_MN, bool B_MN, int BN, int ELT, bool XACT>
 __global__ void __maxnreg__(224)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmD,
@@ -678,7 +681,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         side_stage ^= 1;
       };
 
-      if (glu) {
+      if (!XACT && glu) {
         // ---------------- gated-linear-unit epilogues ----------------
         const bool fwd = args.epilogue == EPI_GLU;
         const long long row_off = (static_cast<long long>(tc.g) * args.d_group_stride + static_cast<long long>(m) * args.ldd) * 2;
@@ -719,6 +722,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             else glu_fwd_seg<ACT_SILU>(g, u, o);
             store_seg(&tmD, d_row, n, ncols, o);
           } else {
+            if (args.scale_a != nullptr || args.scale_b != nullptr) {     // fp8 operands: dh = acc * sa[m] * sb[n]
+              const float* sb = args.scale_b != nullptr ? args.scale_b + static_cast<long long>(gb) * args.scale_b_group_stride + n : nullptr;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                r[j] = __float_as_uint(__uint_as_float(r[j]) * ((sb != nullptr && j < ncols) ? sa * sb[j] : sa));
+            }
             side_fetch(c, n, ncols, g, u);
             if (args.act == ACT_RELU) glu_bwd_seg<ACT_RELU>(r, g, u, o);
             else if (args.act == ACT_GELU) glu_bwd_seg<ACT_GELU>(r, g, u, o);
@@ -752,15 +761,31 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= args.alpha;
           }
-        } else if (args.epilogue == EPI_RELU_BWD || args.epilogue == EPI_ADD) {
+        } else if (args.epilogue == EPI_RELU_BWD || args.epilogue == EPI_ADD || args.epilogue == EPI_ACT_BWD) {
           float f[32];
           side_fetch(c, n, ncols, f, nullptr);
           if (args.epilogue == EPI_RELU_BWD) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = f[j] > 0.0f ? v[j] : 0.0f;
-          } else {
+          } else if (args.epilogue == EPI_ADD) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += f[j];
+          } else if (!XACT) {
+          } else if (args.act == ACT_GELU) {      // f = pre-activation: d/dx [x * Phi(x)] = Phi(x) + x * phi(x)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float cdf = 0.5f * (1.0f + erff(f[j] * 0.70710678118654752f));
+              v[j] *= cdf + f[j] * 0.3989422804014327f * __expf(-0.5f * f[j] * f[j]);
+            }
+          } else if (args.act == ACT_SILU) {      // d/dx [x * s(x)] = s(x) * (1 + x * (1 - s(x)))
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float sg = fast_sigmoid(f[j]);
+              v[j] *= sg * (1.0f + f[j] * (1.0f - sg));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = f[j] > 0.0f ? v[j] : 0.0f;
           }
         } else {
           if (bias_g != nullptr) {
@@ -781,13 +806,19 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
           }
+          if (XACT && args.d2 != nullptr && (args.epilogue == EPI_BIAS_GELU || args.epilogue == EPI_BIAS_SILU)) {
+            // training: the backward pass needs the pre-activation (ReLU gets by with the sign of its output)
+            uint8_t* d2_row = reinterpret_cast<uint8_t*>(args.d2) +
+                              (static_cast<long long>(tc.g) * args.d_group_stride + static_cast<long long>(m) * args.ldd) * 2;
+            store_seg(&tmD2, d2_row, n, ncols, v);
+          }
           if (args.epilogue == EPI_BIAS_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-          } else if (args.epilogue == EPI_BIAS_GELU) {
+          } else if (XACT && args.epilogue == EPI_BIAS_GELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          } else if (args.epilogue == EPI_BIAS_SILU) {
+          } else if (XACT && args.epilogue == EPI_BIAS_SILU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
           }
@@ -938,11 +969,11 @@ struct OutMaps {
   CUtensorMap d, d2, d3, x, x2;   // outputs and side inputs (32x32 blocks, SWIZZLE_64B)
 };
 
-template <int CG, bool A_MN, bool B_MN, int BN, int ELT>
+template <int CG, bool A_MN, bool B_MN, int BN, int ELT, bool XACT = false>
 cudaError_t launch_inst(const CUtensorMap& ta, const CUtensorMap& tb_, const CUtensorMap& tb2, const OutMaps& om,
                         const GemmArgs& args_in, int grid, cudaStream_t stream) {
   using C = Cfg<CG, BN>;
-  auto* kern = gemm_sm100_kernel<CG, A_MN, B_MN, BN, ELT>;
+  auto* kern = gemm_sm100_kernel<CG, A_MN, B_MN, BN, ELT, XACT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
@@ -1059,7 +1090,7 @@ cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const c
     if (p.d3 != nullptr && !make_output_map(&om.d3, p.d3, p.out_dtype, p.M, p.N, p.ldd, p.d_group_stride, p.G, why))
       return cudaErrorInvalidValue;
     a.tma_store = 1;
-    const bool uses_side = p.epilogue == EPI_RELU_BWD || p.epilogue == EPI_ADD || p.epilogue == EPI_GLU_BWD;
+    const bool uses_side = p.epilogue == EPI_RELU_BWD || p.epilogue == EPI_ADD || p.epilogue == EPI_GLU_BWD || p.epilogue == EPI_ACT_BWD;
     if (uses_side && p.aux != nullptr && ((reinterpret_cast<uintptr_t>(p.aux) | reinterpret_cast<uintptr_t>(p.aux2)) & 15) == 0 &&
         ((p.ld_aux * 2) & 15) == 0 && ((p.aux_group_stride * 2) & 15) == 0) {
       if (!make_output_map(&om.x, p.aux, p.out_dtype, p.M, p.N, p.ld_aux, p.aux_group_stride, p.G, why)) return cudaErrorInvalidValue;
@@ -1073,7 +1104,13 @@ cudaError_t gemm_sm100_launch(const GemmProblem& p, cudaStream_t stream, const c
   int grid = static_cast<int>(want < sms ? want : sms);
   if (cg == 2 && (grid & 1)) grid += 1;
 
-#define TB_LAUNCH(CGv, AMN, BMN, BNv) return launch_inst<CGv, AMN, BMN, BNv, 2>(ta, tb_, tb2, om, a, grid, stream)
+  const bool xact = p.epilogue == EPI_BIAS_GELU || p.epilogue == EPI_BIAS_SILU || p.epilogue == EPI_ACT_BWD;
+  if (xact && eb != 2) { *why = "GELU / SiLU epilogues need 16-bit operands"; return cudaErrorInvalidValue; }
+#define TB_LAUNCH(CGv, AMN, BMN, BNv)                                                                   \
+  do {                                                                                                  \
+    if (xact) return launch_inst<CGv, AMN, BMN, BNv, 2, true>(ta, tb_, tb2, om, a, grid, stream);        \
+    return launch_inst<CGv, AMN, BMN, BNv, 2, false>(ta, tb_, tb2, om, a, grid, stream);                 \
+  } while (0)
 #define TB_SWITCH_MAJOR(CGv, BNv)                                    \
   do {                                                               \
     if (!p.a_mn_major && !p.b_mn_major) TB_LAUNCH(CGv, false, false, BNv); \

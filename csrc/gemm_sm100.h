@@ -9,12 +9,13 @@ enum GemmEpilogue : int {
   EPI_NONE = 0,       // D = acc * alpha
   EPI_BIAS = 1,       // D = acc + bias[n]
   EPI_BIAS_RELU = 2,  // D = relu(acc + bias[n])        (bias optional)
-  EPI_BIAS_GELU = 3,  // D = gelu_erf(acc + bias[n])
-  EPI_BIAS_SILU = 4,  // D = silu(acc + bias[n])
+  EPI_BIAS_GELU = 3,  // D = gelu_erf(acc + bias[n])      (d2, when given, receives the pre-activation acc + bias)
+  EPI_BIAS_SILU = 4,  // D = silu(acc + bias[n])          (same)
   EPI_RELU_BWD = 5,   // D = aux[m,n] > 0 ? acc : 0     (aux = forward activation output)
   EPI_GLU = 6,        // dual-B: D = act(A*B) .* (A*B2); optionally also stores g = A*B -> d2 and u = A*B2 -> d3
   EPI_GLU_BWD = 7,    // acc = dh:  D = dh * u * act'(g)  and  d2 = dh * act(g)   with g = aux, u = aux2
   EPI_ADD = 8,        // D = acc + aux[m,n]
+  EPI_ACT_BWD = 9,    // D = acc * act'(aux[m,n])        (aux = forward PRE-activation; act = GemmProblem::act)
 };
 
 enum GemmAct : int { ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3 };

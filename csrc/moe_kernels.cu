@@ -202,7 +202,7 @@ encode_rows_kernel(const T* __restrict__ x, const float* __restrict__ gates, con
                    T* __restrict__ out, const unsigned long long* __restrict__ dst_ptr_table,
                    const unsigned long long* __restrict__ signal_ptr_table, unsigned int* __restrict__ chunk_counters,
                    int chunk_rows, int unit_rows, int S, int E, int k, int C, int M, int rot_units,
-                   uint32_t signal_value) {
+                   uint32_t signal_value, const int* __restrict__ valid_rows) {
   // Work unit = `unit_rows` consecutive slots of one expert (one warp per row).  Many blocks cooperate on one flag
   // chunk (`chunk_rows` rows); the block that finishes the chunk's last unit publishes the flag.
   constexpr int kEncWarps = THREADS / 32;
@@ -215,7 +215,8 @@ encode_rows_kernel(const T* __restrict__ x, const float* __restrict__ gates, con
     const long long u = (ui + rot_units) % total_units;
     const int e = static_cast<int>(u / units_per_expert);
     const int r0 = static_cast<int>(u - static_cast<long long>(e) * units_per_expert) * unit_rows;
-    const int r1 = min(r0 + unit_rows, C);
+    int r1 = min(r0 + unit_rows, C);
+    if (valid_rows != nullptr) r1 = min(r1, valid_rows[e]);   // dropless bound buffers: rows past the count are never read
     T* dst_e = dst_ptr_table != nullptr ? reinterpret_cast<T*>(dst_ptr_table[e])
                                         : out + static_cast<long long>(e) * C * M;
     for (int r = r0 + warp; r < r1; r += kEncWarps) {
@@ -436,6 +437,123 @@ quantize_rows_kernel(const T* __restrict__ x, uint8_t* __restrict__ q, float* __
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp8 dispatch: encode (slot-centric gather) + per-row e4m3 quantisation + optional remote push, one warp per row.
+// Destination row = M bytes of e4m3 and one fp32 scale (max|row| / 448) in a separate [E, C] array; the scale factors out
+// of the expert GEMM's dot product and is applied in its epilogue (scale_a).  Half the NVLink bytes of a 16-bit push.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS, 65536 / (THREADS * 64))
+encode_rows_fp8_kernel(const T* __restrict__ x, const float* __restrict__ gates, const int* __restrict__ slot_src,
+                       uint8_t* __restrict__ out, float* __restrict__ scale_out,
+                       const unsigned long long* __restrict__ dst_ptr_table,
+                       const unsigned long long* __restrict__ scale_ptr_table,
+                       const unsigned long long* __restrict__ signal_ptr_table, unsigned int* __restrict__ chunk_counters,
+                       int chunk_rows, int unit_rows, int S, int E, int k, int C, int M, int rot_units,
+                       uint32_t signal_value) {
+  static_assert(Vec<T>::N == 8, "16-bit sources only");
+  constexpr int kWarps = THREADS / 32;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int units_per_expert = (C + unit_rows - 1) / unit_rows;
+  const int chunks_per_expert = (C + chunk_rows - 1) / chunk_rows;
+  const long long total_units = static_cast<long long>(E) * units_per_expert;
+  const int n16 = M / 16;                                    // 16-element groups per row (M % 16 == 0)
+  for (long long ui = blockIdx.x; ui < total_units; ui += gridDim.x) {
+    const long long u = (ui + rot_units) % total_units;
+    const int e = static_cast<int>(u / units_per_expert);
+    const int r0 = static_cast<int>(u - static_cast<long long>(e) * units_per_expert) * unit_rows;
+    const int r1 = min(r0 + unit_rows, C);
+    uint8_t* dst_e = dst_ptr_table != nullptr ? reinterpret_cast<uint8_t*>(dst_ptr_table[e])
+                                              : out + static_cast<long long>(e) * C * M;
+    float* sc_e = scale_ptr_table != nullptr ? reinterpret_cast<float*>(scale_ptr_table[e])
+                                             : scale_out + static_cast<long long>(e) * C;
+    for (int r = r0 + warp; r < r1; r += kWarps) {
+      const int src = slot_src[static_cast<long long>(e) * C + r];
+      uint4* drow = reinterpret_cast<uint4*>(dst_e + static_cast<long long>(r) * M);
+      if (src < 0) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (int v = lane; v < n16; v += 32) ptx::st_na_v4(drow + v, z);
+        if (lane == 0) sc_e[r] = 1.0f;
+        continue;
+      }
+      const int tok = src / k;
+      const int j = src - tok * k;
+      const float g = gates != nullptr ? gates[static_cast<long long>(j) * S + tok] : 1.0f;
+      const uint4* sv = reinterpret_cast<const uint4*>(x + static_cast<long long>(tok) * M);
+      float amax = 0.0f;
+      for (int v = lane; v < 2 * n16; v += 32) {
+        float f[8];
+        Vec<T>::unpack(ptx::ld_v4(sv + v), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(f[i]));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      amax *= fabsf(g);
+      const float sc = amax > 0.0f ? amax * (1.0f / 448.0f) : 1.0f;
+      const float inv = g / sc;
+      if (lane == 0) sc_e[r] = sc;
+      for (int v = lane; v < n16; v += 32) {                 // second pass hits L1/L2: 2 x 16 B in, 16 B out
+        float f[16];
+        Vec<T>::unpack(ptx::ld_v4(sv + 2 * v), f);
+        Vec<T>::unpack(ptx::ld_v4(sv + 2 * v + 1), f + 8);
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __nv_fp8x4_e4m3 p4(make_float4(f[4 * i] * inv, f[4 * i + 1] * inv, f[4 * i + 2] * inv, f[4 * i + 3] * inv));
+          w[i] = *reinterpret_cast<const uint32_t*>(&p4);
+        }
+        ptx::st_na_v4(drow + v, make_uint4(w[0], w[1], w[2], w[3]));
+      }
+    }
+    if (signal_ptr_table != nullptr) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int ci = r0 / chunk_rows;
+        const int chunk_begin = ci * chunk_rows;
+        const int chunk_end = min(chunk_begin + chunk_rows, C);
+        const unsigned units_in_chunk = static_cast<unsigned>((chunk_end - chunk_begin + unit_rows - 1) / unit_rows);
+        unsigned int* cnt = chunk_counters + static_cast<long long>(e) * chunks_per_expert + ci;
+        unsigned prev;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(cnt) : "memory");
+        if (prev == units_in_chunk - 1u) {
+          *cnt = 0u;
+          uint32_t* flag = reinterpret_cast<uint32_t*>(signal_ptr_table[e]) + ci;
+          ptx::fence_acq_rel_sys();
+          if (signal_value != 0u) ptx::st_release_sys(flag, signal_value);
+          else ptx::red_add_release_sys(flag, 1u);
+        }
+      }
+    }
+  }
+}
+
+// y[r, :] = float(q[r, :]) * scale[r]   (e4m3 rows back to 16 bit: received fp8 activations feed 16-bit weight-gradient GEMMs)
+template <typename T>
+__global__ void __launch_bounds__(256)
+dequant_rows_kernel(const uint8_t* __restrict__ q, const float* __restrict__ scale, T* __restrict__ y, long long R, int K) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long r = static_cast<long long>(blockIdx.x) * 8 + warp; r < R; r += static_cast<long long>(gridDim.x) * 8) {
+    const float sc = scale[r];
+    const uint4* qrow = reinterpret_cast<const uint4*>(q + r * K);
+    uint4* yrow = reinterpret_cast<uint4*>(y + r * K);
+    for (int v = lane; v < K / 16; v += 32) {
+      const uint4 u = ptx::ld_nc_v4(qrow + v);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_fp8x4_e4m3 p4 = *reinterpret_cast<const __nv_fp8x4_e4m3*>(&w[i]);
+        const float4 t = static_cast<float4>(p4);
+        f[4 * i] = t.x * sc; f[4 * i + 1] = t.y * sc; f[4 * i + 2] = t.z * sc; f[4 * i + 3] = t.w * sc;
+      }
+      ptx::st_na_v4(yrow + 2 * v, Vec<T>::pack(f));
+      ptx::st_na_v4(yrow + 2 * v + 1, Vec<T>::pack(f + 8));
+    }
+  }
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -477,7 +595,7 @@ template <typename T>
 static cudaError_t encode_rows_t(const void* x, const void* gates, const int* slot_src, void* out,
                                  const unsigned long long* dst_ptr_table, const unsigned long long* signal_ptr_table,
                                  unsigned int* chunk_counters, int signal_rows, int S, int E, int k, int C, int M,
-                                 int rot_chunks, int signal_value, cudaStream_t stream) {
+                                 int rot_chunks, int signal_value, const int* valid_rows, cudaStream_t stream) {
   if (E <= 0 || C <= 0 || M <= 0) return cudaSuccess;
   const int unit_rows = 16;
   int chunk_rows = signal_rows > 0 ? signal_rows : unit_rows;
@@ -494,7 +612,7 @@ static cudaError_t encode_rows_t(const void* x, const void* gates, const int* sl
   encode_rows_kernel<T, VECv, THRv><<<grid, THRv, 0, stream>>>(                                                      \
       static_cast<const T*>(x), static_cast<const float*>(gates), slot_src, static_cast<T*>(out), dst_ptr_table,     \
       signal_ptr_table, chunk_counters, chunk_rows, unit_rows, S, E, k, C, M, rot_units,                             \
-      static_cast<uint32_t>(signal_value))
+      static_cast<uint32_t>(signal_value), valid_rows)
   if (dst_ptr_table != nullptr) {
     if (vec) TB_ENC_LAUNCH(true, kEncPushThreads); else TB_ENC_LAUNCH(false, kEncPushThreads);
   } else {
@@ -507,13 +625,54 @@ static cudaError_t encode_rows_t(const void* x, const void* gates, const int* sl
 cudaError_t encode_rows(const void* x, const void* gates, const int* slot_src, void* out,
                         const unsigned long long* dst_ptr_table, const unsigned long long* signal_ptr_table,
                         unsigned int* chunk_counters, int signal_rows, int S, int E, int k, int C, int M, int elem_type,
-                        int rot_chunks, int signal_value, cudaStream_t stream) {
+                        int rot_chunks, int signal_value, const int* valid_rows, cudaStream_t stream) {
   switch (elem_type) {
-    case ET_F32: return encode_rows_t<float>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, chunk_counters, signal_rows, S, E, k, C, M, rot_chunks, signal_value, stream);
-    case ET_F16: return encode_rows_t<__half>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, chunk_counters, signal_rows, S, E, k, C, M, rot_chunks, signal_value, stream);
-    case ET_BF16: return encode_rows_t<__nv_bfloat16>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, chunk_counters, signal_rows, S, E, k, C, M, rot_chunks, signal_value, stream);
+    case ET_F32: return encode_rows_t<float>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, chunk_counters, signal_rows, S, E, k, C, M, rot_chunks, signal_value, valid_rows, stream);
+    case ET_F16: return encode_rows_t<__half>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, chunk_counters, signal_rows, S, E, k, C, M, rot_chunks, signal_value, valid_rows, stream);
+    case ET_BF16: return encode_rows_t<__nv_bfloat16>(x, gates, slot_src, out, dst_ptr_table, signal_ptr_table, chunk_counters, signal_rows, S, E, k, C, M, rot_chunks, signal_value, valid_rows, stream);
   }
   return cudaErrorInvalidValue;
+}
+
+cudaError_t encode_rows_fp8(const void* x, const void* gates, const int* slot_src, void* out, float* scale_out,
+                            const unsigned long long* dst_ptr_table, const unsigned long long* scale_ptr_table,
+                            const unsigned long long* signal_ptr_table, unsigned int* chunk_counters, int signal_rows, int S,
+                            int E, int k, int C, int M, int elem_type, int rot_chunks, int signal_value, cudaStream_t stream) {
+  if (E <= 0 || C <= 0 || M <= 0) return cudaSuccess;
+  if (M % 16 || (reinterpret_cast<uintptr_t>(x) & 15) || (elem_type != ET_F16 && elem_type != ET_BF16)) return cudaErrorInvalidValue;
+  if (signal_ptr_table != nullptr && chunk_counters == nullptr) return cudaErrorInvalidValue;
+  const int unit_rows = 16;
+  int chunk_rows = signal_rows > 0 ? signal_rows : unit_rows;
+  chunk_rows = (chunk_rows + unit_rows - 1) / unit_rows * unit_rows;
+  const long long units = static_cast<long long>(E) * ((C + unit_rows - 1) / unit_rows);
+  const bool remote = dst_ptr_table != nullptr;
+  const long long cap = (remote ? 2LL : 4LL) * num_sms();
+  const int grid = static_cast<int>(units < cap ? units : cap);
+  const int rot_units = rot_chunks * (chunk_rows / unit_rows);
+#define TB_ENC8(Tv, THRv)                                                                                              \
+  encode_rows_fp8_kernel<Tv, THRv><<<grid, THRv, 0, stream>>>(                                                          \
+      static_cast<const Tv*>(x), static_cast<const float*>(gates), slot_src, static_cast<uint8_t*>(out), scale_out,    \
+      dst_ptr_table, scale_ptr_table, signal_ptr_table, chunk_counters, chunk_rows, unit_rows, S, E, k, C, M, rot_units, \
+      static_cast<uint32_t>(signal_value))
+  if (elem_type == ET_BF16) { if (remote) TB_ENC8(__nv_bfloat16, kEncPushThreads); else TB_ENC8(__nv_bfloat16, kEncThreads); }
+  else { if (remote) TB_ENC8(__half, kEncPushThreads); else TB_ENC8(__half, kEncThreads); }
+#undef TB_ENC8
+  return cudaGetLastError();
+}
+
+cudaError_t dequant_rows_e4m3(const void* q, const float* scale, void* y, long long R, int K, int elem_type,
+                              cudaStream_t stream) {
+  if (R <= 0 || K <= 0) return cudaSuccess;
+  if (K % 16 || (reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return cudaErrorInvalidValue;
+  const long long want = (R + 7) / 8;
+  const int grid = static_cast<int>(want < 16LL * num_sms() ? want : 16LL * num_sms());
+  if (elem_type == ET_BF16)
+    dequant_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const uint8_t*>(q), scale, static_cast<__nv_bfloat16*>(y), R, K);
+  else if (elem_type == ET_F16)
+    dequant_rows_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const uint8_t*>(q), scale, static_cast<__half*>(y), R, K);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
 }
 
 template <typename T>

@@ -26,11 +26,18 @@ cudaError_t build_slot_map(const int* idx, const int* loc, int* slot_src, int S,
 // counter at signal_ptr_table[e] + (r0/signal_rows) is set to `signal_value` with st.release.sys (each chunk has a
 // single publisher - the block that finishes the chunk's last 16-row unit, elected through `chunk_counters`
 // (uint32[E * ceil(C/signal_rows)], zero-initialised, self-resetting) - so the epoch number itself is published;
-// 0 = increment instead).
+// 0 = increment instead).  valid_rows (optional, int[E]): rows >= valid_rows[e] of expert e are left untouched.
 cudaError_t encode_rows(const void* x, const void* gates, const int* slot_src, void* out,
                         const unsigned long long* dst_ptr_table, const unsigned long long* signal_ptr_table,
                         unsigned int* chunk_counters, int signal_rows, int S, int E, int k, int C, int M, int elem_type,
-                        int rot_chunks, int signal_value, cudaStream_t stream);
+                        int rot_chunks, int signal_value, const int* valid_rows, cudaStream_t stream);
+
+// The same gather with per-row e4m3 quantisation: destination rows are M bytes, the row scales (max|row| / 448, fp32) go
+// to scale_out[E*C] or - for a remote push - to scale_ptr_table[e][C].  16-bit sources, M % 16 == 0.
+cudaError_t encode_rows_fp8(const void* x, const void* gates, const int* slot_src, void* out, float* scale_out,
+                            const unsigned long long* dst_ptr_table, const unsigned long long* scale_ptr_table,
+                            const unsigned long long* signal_ptr_table, unsigned int* chunk_counters, int signal_rows, int S,
+                            int E, int k, int C, int M, int elem_type, int rot_chunks, int signal_value, cudaStream_t stream);
 
 // out[s, :] = sum_j w_j * buf[idx_j[s]*C + loc_j[s], :]  (choices with loc >= C or idx < 0 contribute 0).
 // wait_flags (optional): uint32[E] counters that must reach wait_target (acquire.sys) before expert e's rows
@@ -79,10 +86,22 @@ cudaError_t set_spin_timeout_gemm(unsigned long long ns);
 cudaError_t quantize_rows_e4m3(const void* x, void* q, float* scale, long long R, int K, int elem_type,
                                cudaStream_t stream);
 
+// y[r, :] = q[r, :] * scale[r]  (e4m3 -> fp16 / bf16), K % 16 == 0
+cudaError_t dequant_rows_e4m3(const void* q, const float* scale, void* y, long long R, int K, int elem_type,
+                              cudaStream_t stream);
+
 // Dropless / decoder inference: y[g, r, :] = act(x[g, r, :] @ W[g] + bias[g]) for r < counts[g] (device counts, no
 // host sync); x [G, rows_cap, K], y [G, rows_cap, N], W [G, N, K] or (w_is_kn) [G, K, N].  Rows past the count are
 // left untouched.  (csrc/skinny_gemm.cu)
 cudaError_t skinny_grouped_gemm(const void* x, const void* w, const void* bias, void* y, const int* counts, int G,
                                 int rows_cap, int N, int K, bool w_is_kn, bool relu, int elem_type, cudaStream_t stream);
+
+// Whole two-layer expert FFN for a few rows per expert in ONE launch (dropless / decoder inference):
+//   y[g, r, :] += act(x[g, r, :] @ W1[g]^T + b1[g]) @ W2[g] + b2[g]   for r < counts[g]
+// x [G, rows_cap, K], W1 [G, H, K], W2 [G, H, N] (the reference's batched_fc1_w / batched_fc2_w layouts), y fp32
+// [G, rows_cap, N] ZERO-INITIALISED (blocks split H and accumulate with atomics).  act: 0 none, 1 relu, 2 gelu, 3 silu.
+cudaError_t skinny_grouped_ffn(const void* x, const void* w1, const void* b1, const void* w2, const void* b2, float* y,
+                               const int* counts, int G, int rows_cap, int K, int H, int N, int act, int elem_type,
+                               cudaStream_t stream);
 
 }  // namespace tb

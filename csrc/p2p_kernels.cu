@@ -19,9 +19,11 @@
 namespace tb {
 namespace {
 
-constexpr int kPushThreads = 512;
+constexpr int kPushThreadsBig = 512;
+constexpr int kPushThreadsSmall = 128;   // 128 threads x <= 64 registers: fits next to a resident persistent GEMM CTA (gemm_sm100.cu)
 
-__global__ void __launch_bounds__(kPushThreads)
+template <int kPushThreads>
+__global__ void __launch_bounds__(kPushThreads, kPushThreads == 128 ? 8 : 1)
 p2p_push_kernel(const uint8_t* __restrict__ src, const PushPlan plan, const unsigned long long* __restrict__ peer_table,
                 long long recv_heap_off, long long mail_off, long long done_off, long long scratch_off, int rank,
                 int world, uint32_t epoch, int blocks_per_peer) {
@@ -221,12 +223,18 @@ __global__ void p2p_barrier_kernel(const unsigned long long* __restrict__ peer_t
 
 cudaError_t p2p_push(const void* src, const PushPlan& plan, const unsigned long long* peer_table,
                      long long recv_heap_off, long long mail_off, long long done_off, long long scratch_off, int rank,
-                     int world, uint32_t epoch, int blocks_per_peer, cudaStream_t stream) {
+                     int world, uint32_t epoch, int blocks_per_peer, bool small_blocks, cudaStream_t stream) {
   if (world > kMaxPeers) return cudaErrorInvalidValue;
   if (blocks_per_peer < 1) blocks_per_peer = 1;
   const int grid = world * blocks_per_peer;
-  p2p_push_kernel<<<grid, kPushThreads, 0, stream>>>(static_cast<const uint8_t*>(src), plan, peer_table, recv_heap_off,
-                                                     mail_off, done_off, scratch_off, rank, world, epoch, blocks_per_peer);
+  if (small_blocks)     // overlap with a running expert GEMM: blocks that can co-reside with its CTAs
+    p2p_push_kernel<kPushThreadsSmall><<<grid, kPushThreadsSmall, 0, stream>>>(
+        static_cast<const uint8_t*>(src), plan, peer_table, recv_heap_off, mail_off, done_off, scratch_off, rank, world, epoch,
+        blocks_per_peer);
+  else
+    p2p_push_kernel<kPushThreadsBig><<<grid, kPushThreadsBig, 0, stream>>>(
+        static_cast<const uint8_t*>(src), plan, peer_table, recv_heap_off, mail_off, done_off, scratch_off, rank, world, epoch,
+        blocks_per_peer);
   return cudaGetLastError();
 }
 

@@ -26,7 +26,7 @@ struct PushPlan {
 // `epoch` is the 1-based call number on this (ready, done) counter pair.
 cudaError_t p2p_push(const void* src, const PushPlan& plan, const unsigned long long* peer_table,
                      long long recv_heap_off, long long mail_off, long long done_off, long long scratch_off, int rank,
-                     int world, uint32_t epoch, int blocks_per_peer, cudaStream_t stream);
+                     int world, uint32_t epoch, int blocks_per_peer, bool small_blocks, cudaStream_t stream);
 
 // out[i] = sum_p peer_p[stage_off + slice_off + i]  for i in [0, n)   (one-shot pull-reduce; fp32 accumulate).
 // Callers bracket it with p2p_barrier so that all stages are written / may be overwritten.

@@ -208,7 +208,7 @@ void register_symm_bindings(pybind11::module& m) {
   m.def("p2p_collective", [](std::shared_ptr<tb::SymmHeap> h, const at::Tensor& src, std::vector<int64_t> src_off,
                              std::vector<int64_t> dst_off, std::vector<int64_t> nbytes, std::vector<int64_t> out_sizes,
                              int64_t slot_off, int64_t epoch, int64_t blocks_per_peer, int64_t bounce_off,
-                             int64_t bounce_bytes) {
+                             int64_t bounce_bytes, bool small_blocks) {
     TORCH_CHECK(src.is_cuda() && src.is_contiguous());
     const int world = h->world(), rank = h->rank();
     TORCH_CHECK(world <= tb::kMaxPeers && (int)src_off.size() == world && (int)dst_off.size() == world && (int)nbytes.size() == world);
@@ -225,7 +225,7 @@ void register_symm_bindings(pybind11::module& m) {
     tb::PushPlan plan{};
     for (int p = 0; p < world; ++p) { plan.src_off[p] = src_off[p]; plan.dst_off[p] = dst_off[p]; plan.bytes[p] = nbytes[p]; }
     TB_CHECK_CUDA(tb::p2p_push(src.data_ptr(), plan, h->device_peer_table(), off, slot_off, slot_off + 128, slot_off + 256,
-                               rank, world, static_cast<uint32_t>(epoch), static_cast<int>(blocks_per_peer), cur_stream()));
+                               rank, world, static_cast<uint32_t>(epoch), static_cast<int>(blocks_per_peer), small_blocks, cur_stream()));
     uint8_t* ptr = static_cast<uint8_t*>(h->base(rank)) + off;
     auto opts = src.options();
     if (pooled) {
@@ -245,7 +245,7 @@ void register_symm_bindings(pybind11::module& m) {
     for (int p = 0; p < world; ++p) { plan.src_off[p] = src_off[p]; plan.dst_off[p] = dst_off[p]; plan.bytes[p] = nbytes[p]; }
     TB_CHECK_CUDA(tb::p2p_push(src.data_ptr(), plan, reinterpret_cast<const unsigned long long*>(peer_table),
                                dst_heap_off, ready_off, done_off, scratch_off, static_cast<int>(rank), static_cast<int>(world),
-                               static_cast<uint32_t>(epoch), static_cast<int>(blocks_per_peer), cur_stream()));
+                               static_cast<uint32_t>(epoch), static_cast<int>(blocks_per_peer), false, cur_stream()));
   });
   m.def("p2p_reduce_slice", [](at::Tensor& out, int64_t peer_table, int64_t stage_off, int64_t slice_off_bytes,
                                int64_t rank, int64_t world, bool is_max) {

@@ -124,3 +124,80 @@ def test_fast_cumsum_sub_one(S, E):
     mask = (torch.rand(S, E, device='cuda') < 0.3).to(torch.int64)
     out = moe.fast_cumsum_sub_one(mask)
     assert torch.equal(out.long(), torch.cumsum(mask, dim=0) - 1)
+
+
+@pytest.mark.parametrize('dtype,act', [(torch.float32, 'relu'), (torch.bfloat16, 'silu'), (torch.float16, 'gelu')])
+def test_skinny_ffn_matches_torch(C, dtype, act):
+    """Both expert layers in one weight-streaming launch vs fp32 torch (rows past the device-side counts stay zero)."""
+    torch.manual_seed(9)
+    G, R, K, H, N = 5, 12, 256, 200, 136
+    x = torch.randn(G, R, K, device='cuda').to(dtype)
+    w1 = (torch.randn(G, H, K, device='cuda') * 0.1).to(dtype)
+    w2 = (torch.randn(G, H, N, device='cuda') * 0.1).to(dtype)
+    b1, b2 = torch.randn(G, H, device='cuda').to(dtype), torch.randn(G, N, device='cuda').to(dtype)
+    counts = torch.tensor([12, 0, 1, 9, 30], device='cuda', dtype=torch.int32)
+    y = C.skinny_ffn(x, w1, b1, w2, b2, counts, {'relu': 1, 'gelu': 2, 'silu': 3}[act])
+    fn = {'relu': F.relu, 'gelu': F.gelu, 'silu': F.silu}[act]
+    ref = torch.matmul(fn(torch.matmul(x.float(), w1.float().transpose(1, 2)) + b1.float().unsqueeze(1)), w2.float()) + b2.float().unsqueeze(1)
+    mask = (torch.arange(R, device='cuda').view(1, R, 1) < counts.clamp(max=R).view(G, 1, 1))
+    ref = torch.where(mask, ref, torch.zeros((), device='cuda'))
+    tol = 1e-4 if dtype == torch.float32 else 3e-2
+    assert y.dtype == torch.float32 and torch.allclose(y, ref, atol=tol * 4, rtol=tol)
+
+
+def test_dropless_layer_without_host_sync_matches_padded_path(monkeypatch):
+    """capacity_factor=0 + megablocks_size=1 on one GPU: the worst-case row bound (no read-back of the capacity) gives the
+    same output as the dense path with the exact dynamic capacity."""
+    from tutel_b200 import moe
+    torch.manual_seed(0)
+    layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2, 'capacity_factor': 0.0}, model_dim=256,
+                          experts={'type': 'ffn', 'num_experts_per_device': 16, 'hidden_size_per_expert': 512,
+                                   'activation_fn': lambda t: F.relu(t)}, seeds=(1, 1, 1)).cuda().eval()
+    x = torch.randn(1, 24, 256, device='cuda')
+    with torch.no_grad():
+        dense = layer(x)
+        fast = layer(x, megablocks_size=1)
+    assert torch.allclose(dense, fast, atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize('act', ['gelu', 'silu', 'relu'])
+def test_fused_act_ffn_matches_autograd(act):
+    """GELU / SiLU experts on the tcgen05 kernel: the forward epilogue also stores the pre-activation, the dgrad epilogue
+    applies act'(pre) - checked against plain fp32 autograd."""
+    from tutel_b200.ops import gemm as G
+    torch.manual_seed(12)
+    Gn, T, M, H = 2, 384, 256, 512
+    x = (torch.randn(Gn, T, M, device='cuda') * 0.5).bfloat16().requires_grad_(True)
+    w1 = (torch.randn(Gn, H, M, device='cuda') * 0.06).bfloat16().requires_grad_(True)
+    w2 = (torch.randn(Gn, H, M, device='cuda') * 0.06).bfloat16().requires_grad_(True)
+    b1 = (torch.randn(Gn, H, device='cuda') * 0.1).bfloat16().requires_grad_(True)
+    b2 = (torch.randn(Gn, M, device='cuda') * 0.1).bfloat16().requires_grad_(True)
+    y = G.fused_act_ffn(x, w1, b1, w2, b2, None, act)
+    dy = torch.randn_like(y) * 0.1
+    y.backward(dy)
+    fn = {'relu': F.relu, 'gelu': F.gelu, 'silu': F.silu}[act]
+    ps = [t.detach().float().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    yr = torch.matmul(fn(torch.matmul(ps[0], ps[1].transpose(1, 2)) + ps[2].unsqueeze(1)), ps[3]) + ps[4].unsqueeze(1)
+    yr.backward(dy.float())
+
+    def rel(a, b):
+        return ((a.float() - b).norm() / b.norm()).item()
+    errs = [rel(y, yr)] + [rel(t.grad, r.grad) for t, r in zip((x, w1, b1, w2, b2), ps)]
+    assert max(errs) < 0.02, errs
+
+
+def test_graphed_dropless_forward_matches_eager():
+    """The bound-based dropless forward never touches the host, so it can be replayed as one CUDA graph."""
+    from tutel_b200 import moe
+    from tutel_b200.utils.graph import GraphedForward
+    torch.manual_seed(1)
+    layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2, 'capacity_factor': 0.0}, model_dim=128,
+                          experts={'type': 'ffn', 'num_experts_per_device': 32, 'hidden_size_per_expert': 256,
+                                   'activation_fn': lambda t: F.relu(t)}, seeds=(1, 1, 1)).cuda().eval()
+    xs = [torch.randn(1, 16, 128, device='cuda') for _ in range(3)]
+    fast = GraphedForward(lambda t: layer(t, megablocks_size=1), xs[0])
+    for x in xs:
+        with torch.no_grad():
+            want = layer(x, megablocks_size=1)
+        got = fast(x).clone()
+        assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)

@@ -92,7 +92,7 @@ def test_encode_decode_gate_grad_match_cpu(C, dtype, M):
     idx_d, loc_d = idx.cuda(), loc.cuda()
     slot = C.build_slot_map(idx_d, loc_d, E, cap)
     out = torch.empty(E * cap, M, dtype=dtype, device='cuda')
-    C.encode_rows(x.cuda(), gates.cuda(), slot, out, k, E, cap, 0, 0, 0, 0, 0, 0)
+    C.encode_rows(x.cuda(), gates.cuda(), slot, out, k, E, cap, 0, 0, 0, 0, 0, 0, None)
     assert torch.allclose(out.float().cpu(), C.cpu_encode(x.float(), gates, idx, loc, E, cap), atol=tol, rtol=tol)
     dec = C.decode_rows(y.cuda(), gates.cuda(), idx_d, loc_d, E, cap, 0, 0)
     ref = C.cpu_decode(y.float(), gates, idx, loc, E, cap)

@@ -11,11 +11,16 @@ from tutel_b200 import moe, net, system  # noqa: E402
 from tutel_b200.parallel import p2p  # noqa: E402
 
 
+_FAILED = []
+
+
 def check(name, ok):
+    """Record the verdict and keep going: a rank that stopped here would leave its peers waiting in the next collective
+    (main() turns recorded failures into a non-zero exit code on every rank)."""
     r = dist.get_rank()
     print('[rank %d] %s: %s' % (r, name, 'OK' if ok else 'FAIL'), flush=True)
     if not ok:
-        raise SystemExit(3)
+        _FAILED.append(name)
 
 
 def test_collectives(env):
@@ -85,14 +90,17 @@ def test_collectives(env):
 
 
 def run_layer(env, fused, dtype, nle, steps=3, overlap=1, model_dim=256, hidden=512, tokens=512, expert='ffn', act=None,
-              is_postscore=True):
+              is_postscore=True, output_dim=None, parallel_type='adaptive:1', same_experts=False):
     os.environ['TUTEL_B200_FUSED'] = '1' if fused else '0'
     r, dev = env.global_rank, env.local_device
     torch.manual_seed(7)
-    layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2, 'capacity_factor': 1.5}, model_dim=model_dim,
-                          experts={'type': expert, 'num_experts_per_device': nle, 'hidden_size_per_expert': hidden,
-                                   'activation_fn': act or (lambda t: F.relu(t))},
-                          seeds=(1, r + 1, 1), a2a_ffn_overlap_degree=overlap, is_postscore=is_postscore).to(dev).to(dtype)
+    experts = {'type': expert, 'num_experts_per_device': nle, 'hidden_size_per_expert': hidden,
+               'activation_fn': act or (lambda t: F.relu(t))}
+    if output_dim is not None:
+        experts['output_dim'] = output_dim
+    layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2, 'capacity_factor': 1.5}, model_dim=model_dim, experts=experts,
+                          seeds=(1, 1 if same_experts else r + 1, 1), a2a_ffn_overlap_degree=overlap, is_postscore=is_postscore,
+                          parallel_type=parallel_type).to(dev).to(dtype)
     opt = torch.optim.SGD(layer.parameters(), lr=1e-2)
     torch.manual_seed(50 + r)
     x = torch.randn(tokens, model_dim, device=dev).to(dtype)
@@ -120,13 +128,23 @@ def test_fused_vs_nccl(env):
                 if not ok:
                     print('losses', a[0], b[0], (a[2] - b[2]).abs().max().item(), (a[1] - b[1]).abs().max().item(), flush=True)
                 check('fused==nccl nle=%d d=%d' % (nle, overlap), ok)
-    if os.environ.get('TUTEL_B200_FUSED_PRESCORE', '0') == '1':     # opt-in until it has run once on real GPUs
-        for expert in ('ffn', 'llama_ffn'):
-            a = run_layer(env, True, torch.bfloat16, 1, expert=expert, is_postscore=False)
-            b = run_layer(env, False, torch.bfloat16, 1, expert=expert, is_postscore=False)
-            ok = all(abs(u - v) <= 2e-2 * max(1.0, abs(v)) for u, v in zip(a[0], b[0]))
-            ok = ok and torch.allclose(a[2], b[2], atol=3e-2, rtol=3e-2) and torch.allclose(a[1], b[1], atol=3e-2, rtol=5e-2)
-            check('fused==nccl prescore %s' % expert, ok)
+    # every mode the engine covers: pre-score gating, other activations, output_dim, experts sharded over the GPUs
+    W = env.global_size
+    modes = [('prescore ffn', dict(expert='ffn', is_postscore=False)), ('prescore llama_ffn', dict(expert='llama_ffn', is_postscore=False)),
+             ('gelu', dict(act=F.gelu)), ('silu', dict(act=lambda t: F.silu(t))), ('output_dim', dict(output_dim=128)),
+             ('sharded r=1 (data)', dict(nle=-W, parallel_type='data', hidden=512, same_experts=True)),
+             ('sharded r=W (model)', dict(nle=-W, parallel_type='model', hidden=512, same_experts=True)),
+             ('sharded llama_ffn', dict(nle=-W, expert='llama_ffn', act=F.silu, same_experts=True))]
+    for name, kw in modes:
+        kw = dict(kw)
+        nle = kw.pop('nle', 1)
+        a = run_layer(env, True, torch.bfloat16, nle, **kw)
+        b = run_layer(env, False, torch.bfloat16, nle, **kw)
+        ok = all(abs(u - v) <= 2e-2 * max(1.0, abs(v)) for u, v in zip(a[0], b[0]))
+        ok = ok and torch.allclose(a[2], b[2], atol=3e-2, rtol=3e-2) and torch.allclose(a[1], b[1], atol=3e-2, rtol=5e-2)
+        if not ok:
+            print(name, 'losses', a[0], b[0], (a[2] - b[2]).abs().max().item(), (a[1] - b[1]).abs().max().item(), flush=True)
+        check('fused==generic %s' % name, ok)
     # gated (SwiGLU) experts through the same engine
     for nle, act in ((1, F.silu), (2, None)):
         a = run_layer(env, True, torch.bfloat16, nle, expert='llama_ffn', act=act)
@@ -187,6 +205,40 @@ def test_2dh(env):
     for tag, o in (('2dh d=1', outs[1]), ('2dh d=2 (async phases)', outs[2])):
         check('layer %s == flat' % tag, all(torch.allclose(a, b, atol=1e-5, rtol=1e-4) for a, b in zip(o, outs[0])))
     os.environ['TUTEL_B200_FUSED'] = '1'
+
+
+def test_deep_stack(env):
+    """Six MoE layers share ONE ring of three buffer sets: every layer's lease is spilled when the ring wraps, and the
+    result must match the generic path (which keeps everything in ordinary tensors)."""
+    r, dev = env.global_rank, env.local_device
+    from tutel_b200.parallel import fused as fused_mod
+    outs = []
+    for fused in (True, False):
+        os.environ['TUTEL_B200_FUSED'] = '1' if fused else '0'
+        torch.manual_seed(7)
+        layers = torch.nn.ModuleList([
+            moe.moe_layer(gate_type={'type': 'top', 'k': 2, 'capacity_factor': 1.25}, model_dim=256,
+                          experts={'type': 'ffn', 'num_experts_per_device': 2, 'hidden_size_per_expert': 512,
+                                   'activation_fn': lambda t: F.relu(t)}, seeds=(1, r + 1, 1)) for _ in range(6)]).to(dev).bfloat16()
+        torch.manual_seed(50 + r)
+        x = torch.randn(512, 256, device=dev).bfloat16().requires_grad_(True)
+        h = x
+        for layer in layers:
+            h = h + layer(h)
+        h.float().pow(2).mean().backward()
+        outs.append((h.float().detach(), x.grad.float().clone(), layers[0].experts.batched_fc1_w.grad.float().clone(),
+                     layers[5].experts.batched_fc2_w.grad.float().clone()))
+        if fused:
+            t = p2p.transport_for(None)
+            rings = [rg for rg in fused_mod._engine(t).rings.values() if rg is not None]
+            check('one shared ring of <= 3 sets for 6 layers', len(rings) >= 1 and all(len(rg.sets) <= 3 for rg in rings))
+    os.environ['TUTEL_B200_FUSED'] = '1'
+
+    def rel(a, b):
+        return ((a - b).norm() / (b.norm() + 1e-12)).item()
+    errs = [rel(a, b) for a, b in zip(outs[0], outs[1])]
+    print('[rank %d] deep stack rel errors %s' % (r, errs), flush=True)
+    check('6-layer stack fused == generic', max(errs) < 3e-2)
 
 
 def _oracle_pair(env, nle, expert, tokens, model_dim, hidden, k=2, act=None):
@@ -277,6 +329,8 @@ def main():
         test_fused_vs_nccl(env)
     if which in ('all', 'oracle'):
         test_oracle(env)
+    if which in ('all', 'deep'):
+        test_deep_stack(env)
     if which in ('all', 'equiv'):
         test_parallel_equivalence(env)
     if which in ('sub',) or (which == 'all' and env.global_size >= 4):
@@ -289,9 +343,19 @@ def main():
         net.simple_all_to_all(a)
         torch.cuda.synchronize()
         print('FIRST_OK', flush=True)
-        net.simple_all_to_all(a)
-        torch.cuda.synchronize()     # raises on the surviving ranks (device trap after the bounded spin)
-    dist.barrier()
+        try:
+            net.simple_all_to_all(a)
+            torch.cuda.synchronize()     # raises on the surviving ranks (device trap after the bounded spin)
+            import time
+            time.sleep(20)               # the rank that skipped its push: wait for the launcher to tear the job down
+        finally:
+            sys.stdout.flush()
+            os._exit(17)                 # the CUDA context is gone: no destructors, no NCCL teardown
+    bad = torch.tensor([len(_FAILED)], device=env.local_device)
+    dist.all_reduce(bad)
+    if int(bad.item()) > 0:
+        print('[rank %d] FAILED checks: %s' % (env.global_rank, _FAILED), flush=True)
+        raise SystemExit(3)
     if env.global_rank == 0:
         print('WORKER_OK', flush=True)
 

@@ -118,8 +118,11 @@ class FusedExpertsNetwork(torch.nn.Module):
         row_counts = None
         if getattr(ctx, 'megablocks_size', 0) > 0:
             mb = ctx.megablocks_size
-            groups = torch.div(ctx.dispatch_count + (mb - 1), mb, rounding_mode='floor')
-            row_counts = (torch.clamp(groups, max=x.size(1) // mb) * mb).to(torch.int32)
+            if mb == 1 and ctx.dispatch_count.dtype == torch.int32:
+                row_counts = ctx.dispatch_count          # the kernels clamp to the buffer's rows themselves: no extra launches
+            else:
+                groups = torch.div(ctx.dispatch_count + (mb - 1), mb, rounding_mode='floor')
+                row_counts = (torch.clamp(groups, max=x.size(1) // mb) * mb).to(torch.int32)
         w1, b1, w2, b2 = self.materialize(ctx)
         return self.compute(x, w1, b1, w2, b2, row_counts)
 
@@ -127,18 +130,20 @@ class FusedExpertsNetwork(torch.nn.Module):
         lead = x.shape
         if x.dim() > 3:
             x = x.reshape(x.size(0), x.size(1), -1)
+        if row_counts is not None and G.can_use_skinny_ffn(x, w1, w2, self._act_kind):
+            # dropless decoder inference: a few tokens per expert -> ONE launch streams the active experts' weights once
+            return G.skinny_ffn(x, w1, b1, w2, b2, row_counts, self._act_kind)
         if row_counts is not None and G.can_use_skinny(x, w1):
-            # dropless decoder inference: a few tokens per expert -> stream only the active experts' weights once
             relu = self._act_kind == 'relu'
             y = G.skinny_linear(x, w1, b1, 'nk', row_counts, relu=relu)
             if not relu:
                 y = self.activation_fn(y)
             return G.skinny_linear(y, w2, b2, 'kn', row_counts)
-        if self._act_kind == 'relu' and G.can_use_tcgen05(x, w1) and G.can_use_tcgen05(x, w2):
-            if self.fp8 and x.size(-1) % 16 == 0 and w1.size(1) % 16 == 0:
+        if self._act_kind in G.FWD_EPILOGUE and G.can_use_tcgen05(x, w1) and G.can_use_tcgen05(x, w2):
+            if self.fp8 and self._act_kind == 'relu' and x.size(-1) % 16 == 0 and w1.size(1) % 16 == 0:
                 y = G.fused_relu_ffn_fp8(x, w1, b1, w2, b2, row_counts)
             else:
-                y = G.fused_relu_ffn(x, w1, b1, w2, b2, row_counts)
+                y = G.fused_act_ffn(x, w1, b1, w2, b2, row_counts, self._act_kind)
         else:
             y = G.grouped_linear(x, w1, b1, 'nk', row_counts)
             y = self.activation_fn(y)

@@ -262,8 +262,18 @@ class MOELayer(torch.nn.Module):
         if cuda_fused or (self.is_gshard_loss and gate_mode == 'force' and logits_w_noise.dim() == 2):
             if cuda_fused:
                 # CUDA: gate + routing in two launches, gate backward in one (ops/gating.py, csrc/gate_route.cu)
-                crit, l_aux = fused_extract_critical(logits_w_noise, top_k, capacity_factor or gctx.capacity_factor,
-                                                     self.normalize_gate, alignment, self.group, inequivalent_tokens)
+                cf = capacity_factor or gctx.capacity_factor
+                bound = 0
+                if cf <= 0 and megablocks_size > 0 and self.world_size == 1 and not inequivalent_tokens:
+                    # single-GPU dropless inference: a worst-case row bound replaces the host read-back of the capacity
+                    S = int(logits_w_noise.size(0))
+                    budget = int(os.environ.get('TUTEL_B200_DROPLESS_BOUND_MB', 512)) << 20
+                    if S * self.num_global_experts * self.model_dim * x.element_size() <= budget:
+                        bound = S
+                crit, l_aux = fused_extract_critical(logits_w_noise, top_k, cf, self.normalize_gate, alignment, self.group,
+                                                     inequivalent_tokens, rows_bound=bound)
+                if getattr(crit, 'skip_padding', False) and not hasattr(self.experts, 'batched_fc1_w'):
+                    crit.skip_padding = False      # custom experts see every row of the buffer: keep the zero padding
                 return logits.dtype, crit, l_aux
             # same formulas, op by op (CPU, batch-prioritised routing): one autograd node for softmax + top-k + loss
             fused_gate = fused_topk_gate(logits_w_noise, k_eff, self.normalize_gate, True)

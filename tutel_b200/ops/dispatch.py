@@ -32,6 +32,7 @@ class DispatchPlan:
         self.loc_ks = loc_ks.contiguous()
         self.k, self.S = int(idx_ks.size(0)), int(idx_ks.size(1))
         self._slot_src = slot_src
+        self.valid_rows = None        # int32 [E]: when set, encode leaves rows past the per-expert count untouched
 
     @property
     def slot_src(self) -> torch.Tensor:
@@ -44,7 +45,9 @@ class DispatchPlan:
         if isinstance(crit, CriticalData):
             plan = getattr(crit, '_plan', None)
             if plan is None:
-                plan = DispatchPlan(crit[0], crit[4], crit.idx_ks, crit.loc_ks)
+                plan = DispatchPlan(crit[0], crit[4], crit.idx_ks, crit.loc_ks, crit._slot_src)
+                if getattr(crit, 'skip_padding', False):
+                    plan.valid_rows = crit[5]
                 crit._plan = plan
             return plan
         E, indices_s, locations_s, _, capacity = crit[0], crit[1], crit[2], crit[3], crit[4]
@@ -79,7 +82,7 @@ def raw_encode(x: torch.Tensor, gates: Optional[torch.Tensor], plan: DispatchPla
         out = torch.empty([plan.E * plan.C, M], dtype=x.dtype, device=x.device)
         g = None if gates is None else gates.to(torch.float32).contiguous()
         backend.count_launch()
-        backend.require_ext().encode_rows(x, g, plan.slot_src, out, plan.k, plan.E, plan.C, 0, 0, 0, 0, 0, 0)
+        backend.require_ext().encode_rows(x, g, plan.slot_src, out, plan.k, plan.E, plan.C, 0, 0, 0, 0, 0, 0, plan.valid_rows)
         return out
     if _cpu_native(x):
         g = None if gates is None else gates.to(x.dtype).contiguous()

@@ -18,7 +18,8 @@ import torch
 from . import backend
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_GELU, EPI_BIAS_SILU, EPI_RELU_BWD = 0, 1, 2, 3, 4, 5
-EPI_GLU, EPI_GLU_BWD, EPI_ADD = 6, 7, 8
+EPI_GLU, EPI_GLU_BWD, EPI_ADD, EPI_ACT_BWD = 6, 7, 8, 9
+FWD_EPILOGUE = {'relu': EPI_BIAS_RELU, 'gelu': EPI_BIAS_GELU, 'silu': EPI_BIAS_SILU}
 ACT_CODES = {'relu': 1, 'gelu': 2, 'silu': 3}
 
 
@@ -41,7 +42,8 @@ def raw_gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool
              block_n: int = 0, d_ptr_table: int = 0, signal_ptr_table: int = 0, wait_flags: int = 0,
              wait_rows_per_flag: int = 0, wait_flags_per_group: int = 0, wait_target: int = 0,
              max_ctas: int = 0, group_rot: int = 0, group_mod: int = 1, scale_a: Optional[torch.Tensor] = None,
-             scale_b: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+             scale_b: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
+             d2: Optional[torch.Tensor] = None, act: int = 0) -> torch.Tensor:
     """D[g] = epilogue(A[g] @ B[g // b_group_div]).
 
     ``a``: ``[G, M, K]`` (or ``[G, K, M]`` when ``a_mn``);  ``b``: ``[Gb, N, K]`` (or ``[Gb, K, N]`` when ``b_mn``).
@@ -64,9 +66,10 @@ def raw_gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool
     if aux is not None:
         aux = _prep(aux)
     backend.count_launch()
-    C.gemm(a, b, d, a_mn, b_mn, epilogue, bias, aux, row_counts, float(alpha), int(b_group_div), int(cta_group),
-           int(block_n), int(d_ptr_table), int(signal_ptr_table), int(wait_flags), int(wait_rows_per_flag),
-           int(wait_flags_per_group), int(wait_target), int(max_ctas), int(group_rot), int(group_mod), scale_a, scale_b, colsum)
+    C.gemm_ex(a, b, d, a_mn, b_mn, epilogue, bias, aux, row_counts, float(alpha), int(b_group_div), int(cta_group),
+              int(block_n), int(d_ptr_table), int(signal_ptr_table), int(wait_flags), int(wait_rows_per_flag),
+              int(wait_flags_per_group), int(wait_target), int(max_ctas), int(group_rot), int(group_mod), scale_a, scale_b, colsum,
+              d2, int(act))
     return out
 
 
@@ -146,33 +149,43 @@ def grouped_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor
 
 
 class FusedReluFFN(torch.autograd.Function):
-    """y = relu(x @ W1^T + b1) @ W2 + b2 with 2 forward and 4 backward launches, nothing else.
+    """y = act(x @ W1^T + b1) @ W2 + b2 with 2 forward and 4 backward launches, nothing else (act: relu / gelu / silu).
 
     ``w1 [G, H, M]`` (nk), ``w2 [G, H, Mout]`` (kn) - the reference's ``batched_fc1_w`` / ``batched_fc2_w`` layout.
-    Forward keeps only the post-ReLU activation; its sign doubles as the ReLU mask fused into the dgrad epilogue.
+    ReLU keeps only the post-activation tensor (its sign doubles as the gradient mask fused into the dgrad epilogue);
+    GELU / SiLU also store the pre-activation from the same epilogue and apply act'(pre) in the dgrad epilogue.
     """
 
     @staticmethod
-    def forward(ctx: Any, x, w1, b1, w2, b2, row_counts):
-        act = raw_gemm(x, w1, epilogue=EPI_BIAS_RELU, bias=b1, row_counts=row_counts)
+    def forward(ctx: Any, x, w1, b1, w2, b2, row_counts, act_kind='relu'):
+        need_grad = any(ctx.needs_input_grad[:5])
+        pre = None
+        if act_kind == 'relu':
+            act = raw_gemm(x, w1, epilogue=EPI_BIAS_RELU, bias=b1, row_counts=row_counts)
+        else:
+            pre = torch.empty([x.size(0), x.size(1), w1.size(1)], dtype=x.dtype, device=x.device) if need_grad else None
+            act = raw_gemm(x, w1, epilogue=FWD_EPILOGUE[act_kind], bias=b1, row_counts=row_counts, d2=pre)
         y = raw_gemm(act, w2, b_mn=True, epilogue=EPI_BIAS if b2 is not None else EPI_NONE, bias=b2,
                      row_counts=row_counts)
-        ctx.save_for_backward(x, w1, w2, act)
-        ctx.has_b1, ctx.has_b2 = b1 is not None, b2 is not None
+        ctx.save_for_backward(x, w1, w2, act, pre)
+        ctx.has_b1, ctx.has_b2, ctx.act_kind = b1 is not None, b2 is not None, act_kind
         ctx.row_counts = row_counts
         return y
 
     @staticmethod
     def backward(ctx: Any, dy: torch.Tensor):
-        x, w1, w2, act = ctx.saved_tensors
+        x, w1, w2, act, pre = ctx.saved_tensors
         rc = ctx.row_counts
         dy = dy if _ok_stride(dy) else dy.contiguous()
         if rc is not None:
             dy = _zero_tail(dy, rc)
-        # dh[T,H] = (dy[T,Mout] @ W2^T) * (act > 0)           W2 [H,Mout] is "nk" for this product
+        # dh[T,H] = (dy[T,Mout] @ W2^T) * act'(.)           W2 [H,Mout] is "nk" for this product
         want_db1 = ctx.has_b1 and ctx.needs_input_grad[2]
         db1_acc = torch.zeros([w1.size(0), w1.size(1)], dtype=torch.float32, device=dy.device) if want_db1 else None
-        dh = raw_gemm(dy, w2, epilogue=EPI_RELU_BWD, aux=act, row_counts=rc, colsum=db1_acc)   # db1 fused in the epilogue
+        if ctx.act_kind == 'relu':
+            dh = raw_gemm(dy, w2, epilogue=EPI_RELU_BWD, aux=act, row_counts=rc, colsum=db1_acc)   # db1 fused in the epilogue
+        else:
+            dh = raw_gemm(dy, w2, epilogue=EPI_ACT_BWD, aux=pre, act=ACT_CODES[ctx.act_kind], row_counts=rc, colsum=db1_acc)
         if rc is not None:
             dh = _zero_tail(dh, rc)
             act = _zero_tail(act, rc)
@@ -183,13 +196,16 @@ class FusedReluFFN(torch.autograd.Function):
             dx = _zero_tail(dx, rc)
         dw1 = raw_gemm(dh, x, a_mn=True, b_mn=True) if ctx.needs_input_grad[1] else None        # [H,M] = dh^T @ x
         db1 = db1_acc.to(dh.dtype) if want_db1 else None
-        return dx, dw1, db1, dw2, db2, None
+        return dx, dw1, db1, dw2, db2, None, None
 
 
-def fused_relu_ffn(x, w1, b1, w2, b2, row_counts=None):
+def fused_relu_ffn(x, w1, b1, w2, b2, row_counts=None, act_kind='relu'):
     b1 = None if b1 is None else b1.reshape(w1.size(0), -1)
     b2 = None if b2 is None else b2.reshape(w2.size(0), -1)
-    return FusedReluFFN.apply(x, w1, b1, w2, b2, row_counts)
+    return FusedReluFFN.apply(x, w1, b1, w2, b2, row_counts, act_kind)
+
+
+fused_act_ffn = fused_relu_ffn
 
 
 _PROBE = None
@@ -238,6 +254,26 @@ def can_use_skinny(x: torch.Tensor, w: torch.Tensor) -> bool:
             x.dtype in (torch.float32, torch.float16, torch.bfloat16) and backend.has_cuda_ext())
 
 
+_SKINNY_ACTS = {'relu': 1, 'gelu': 2, 'silu': 3}
+
+
+def can_use_skinny_ffn(x: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, act_kind) -> bool:
+    """Both expert layers in one weight-streaming launch (csrc/skinny_gemm.cu: skinny_ffn_kernel)."""
+    v = 16 // x.element_size()
+    return (can_use_skinny(x, w1) and act_kind in _SKINNY_ACTS and w1.dtype == w2.dtype and w1.size(2) == x.size(2) and
+            w2.size(1) == w1.size(1) and x.size(2) % v == 0 and w2.size(2) % v == 0 and 32 * x.size(2) + 2048 <= 200 * 1024)
+
+
+def skinny_ffn(x, w1, b1, w2, b2, row_counts, act_kind):
+    """y[g, r] = act(x[g, r] @ W1[g]^T + b1[g]) @ W2[g] + b2[g] for r < row_counts[g]; other rows are zero."""
+    backend.count_launch(2)          # zero-fill of the fp32 accumulator + the kernel
+    b1 = None if b1 is None else b1.reshape(w1.size(0), -1).contiguous()
+    b2 = None if b2 is None else b2.reshape(w2.size(0), -1).contiguous()
+    y = backend.require_ext().skinny_ffn(x.contiguous(), w1.contiguous(), b1, w2.contiguous(), b2, row_counts,
+                                         _SKINNY_ACTS[act_kind])
+    return y if y.dtype == x.dtype else y.to(x.dtype)
+
+
 def skinny_linear(x, w, bias, w_layout, row_counts, relu=False):
     """y[g, r] = act(x[g, r] @ W[g] + b[g]) for r < row_counts[g] (csrc/skinny_gemm.cu); other rows are zero."""
     backend.count_launch()
@@ -246,9 +282,29 @@ def skinny_linear(x, w, bias, w_layout, row_counts, relu=False):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# fp8 (e4m3) forward path: per-row activation scales x per-output-channel weight scales, applied in the epilogue
+# fp8 (e4m3) expert GEMMs: per-row (per-token) activation scales x per-output-channel weight scales, applied in the
+# epilogue.  Forward AND data-gradient GEMMs run at the fp8 tensor-core rate; weight gradients stay in 16 bit (their
+# reduction dimension is the token axis, along which the row scales vary).
 # ----------------------------------------------------------------------------------------------------------------
 _FP8_WEIGHT_CACHE = {}
+_FP8_STEP = [0]          # bumped by every optimizer.step() in the process: quantised weights are valid for one step
+_FP8_HOOKED = [False]
+
+
+def invalidate_fp8_cache():
+    """Force re-quantisation of all cached fp8 weights (call after changing weights outside an optimizer step)."""
+    _FP8_STEP[0] += 1
+
+
+def _ensure_step_hook():
+    if _FP8_HOOKED[0]:
+        return
+    _FP8_HOOKED[0] = True
+    try:
+        from torch.optim.optimizer import register_optimizer_step_post_hook
+        register_optimizer_step_post_hook(lambda *_: invalidate_fp8_cache())
+    except Exception:  # noqa - very old torch: fall back to the version counter alone
+        pass
 
 
 def quantize_rows(x: torch.Tensor):
@@ -257,23 +313,31 @@ def quantize_rows(x: torch.Tensor):
     return backend.require_ext().quantize_rows(x.contiguous())
 
 
-def fp8_weight(w: torch.Tensor, layout: str):
-    """K-major e4m3 copy [G, N, K] + per-output-channel scales [G, N] of a weight in 'nk' or 'kn' layout.
-    Cached per (storage, version): weights are re-quantised only after they changed."""
+def fp8_operand(w: torch.Tensor, transpose: bool):
+    """e4m3 copy of ``w [G, R, K]`` (or of ``w^T`` when ``transpose``) quantised along its last dim with one scale per
+    row - the K-major B operand of ``A @ B`` - plus the scales ``[G, R]``.  Cached until the next optimizer step (an
+    optimizer-step hook invalidates the cache: in-place ``.data`` updates do not bump a tensor's version counter) or
+    until the tensor's version changes."""
     import weakref
+    _ensure_step_hook()
     anchor = w._base if w._base is not None else w      # views of a parameter are re-created every forward
-    key = (id(anchor), w.data_ptr(), layout, tuple(w.shape))
-    ver = w._version
+    key = (id(anchor), w.data_ptr(), bool(transpose), tuple(w.shape), tuple(w.stride()))
+    stamp = (w._version, _FP8_STEP[0])
     hit = _FP8_WEIGHT_CACHE.get(key)
-    if hit is not None and hit[0] == ver and hit[3]() is anchor:   # same live tensor, unchanged since quantisation
+    if hit is not None and hit[0] == stamp and hit[3]() is anchor:
         return hit[1], hit[2]
-    wk = w.detach() if layout == 'nk' else w.detach().transpose(1, 2)
-    q, s = quantize_rows(wk.contiguous())
+    src = w.detach().transpose(1, 2) if transpose else w.detach()
+    q, s = quantize_rows(src.contiguous())
     if len(_FP8_WEIGHT_CACHE) > 256:
         for k in [k for k, v in _FP8_WEIGHT_CACHE.items() if v[3]() is None]:
             del _FP8_WEIGHT_CACHE[k]
-    _FP8_WEIGHT_CACHE[key] = (ver, q, s, weakref.ref(anchor))
+    _FP8_WEIGHT_CACHE[key] = (stamp, q, s, weakref.ref(anchor))
     return q, s
+
+
+def fp8_weight(w: torch.Tensor, layout: str):
+    """K-major e4m3 copy [G, N, K] + per-output-channel scales [G, N] of a weight stored 'nk' ([G, N, K]) or 'kn'."""
+    return fp8_operand(w, transpose=(layout == 'kn'))
 
 
 def fp8_linear(x: torch.Tensor, w: torch.Tensor, bias, w_layout: str, epilogue: int = None, row_counts=None):
@@ -286,7 +350,8 @@ def fp8_linear(x: torch.Tensor, w: torch.Tensor, bias, w_layout: str, epilogue: 
 
 
 class FusedReluFFNFp8(torch.autograd.Function):
-    """fp8 forward (2x tensor-core rate), bf16 backward on the master weights (same launches as FusedReluFFN)."""
+    """ReLU FFN with e4m3 forward and data-gradient GEMMs (2x tensor-core rate), 16-bit weight-gradient GEMMs on the
+    master weights.  Quantised weight copies (both orientations) are made once per optimizer step."""
 
     @staticmethod
     def forward(ctx: Any, x, w1, b1, w2, b2, row_counts):
@@ -297,7 +362,34 @@ class FusedReluFFNFp8(torch.autograd.Function):
         ctx.row_counts = row_counts
         return y
 
-    backward = FusedReluFFN.backward
+    @staticmethod
+    def backward(ctx: Any, dy: torch.Tensor):
+        x, w1, w2, act = ctx.saved_tensors
+        rc = ctx.row_counts
+        dy = dy if _ok_stride(dy) else dy.contiguous()
+        if rc is not None:
+            dy = _zero_tail(dy, rc)
+        want_db1 = ctx.has_b1 and ctx.needs_input_grad[2]
+        db1_acc = torch.zeros([w1.size(0), w1.size(1)], dtype=torch.float32, device=dy.device) if want_db1 else None
+        dyq, sdy = quantize_rows(dy)
+        w2q, s2 = fp8_operand(w2, transpose=False)             # dh = dy @ W2^T: W2 [H, Mout] is already K-major for it
+        dh = raw_gemm(dyq, w2q, epilogue=EPI_RELU_BWD, aux=act, row_counts=rc, colsum=db1_acc, out_dtype=dy.dtype,
+                      scale_a=sdy, scale_b=s2)
+        if rc is not None:
+            dh = _zero_tail(dh, rc)
+            act = _zero_tail(act, rc)
+        dw2 = raw_gemm(act, dy, a_mn=True, b_mn=True) if ctx.needs_input_grad[3] else None
+        db2 = column_sums(dy) if ctx.has_b2 and ctx.needs_input_grad[4] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dhq, sdh = quantize_rows(dh)
+            w1q, s1 = fp8_operand(w1, transpose=True)           # dx = dh @ W1: needs W1^T [M, H] K-major
+            dx = raw_gemm(dhq, w1q, row_counts=rc, out_dtype=dy.dtype, scale_a=sdh, scale_b=s1)
+            if rc is not None:
+                dx = _zero_tail(dx, rc)
+        dw1 = raw_gemm(dh, x, a_mn=True, b_mn=True) if ctx.needs_input_grad[1] else None
+        db1 = db1_acc.to(dh.dtype) if want_db1 else None
+        return dx, dw1, db1, dw2, db2, None
 
 
 def fused_relu_ffn_fp8(x, w1, b1, w2, b2, row_counts=None):
@@ -329,13 +421,14 @@ def glu_gemm(a, b, b2, *, b_mn, act, save_pre=False, scale_a=None, scale_b=None,
     return h, g, u
 
 
-def glu_gemm_bwd(dy, w, g, u, *, b_mn, act, row_counts=None, **kw):
-    """(dg, du) for h = act(g) * u with dh = dy @ W formed in TMEM only (never written to memory)."""
+def glu_gemm_bwd(dy, w, g, u, *, b_mn, act, row_counts=None, scale_a=None, scale_b=None, **kw):
+    """(dg, du) for h = act(g) * u with dh = dy @ W formed in TMEM only (never written to memory); dy / W may be e4m3
+    with per-row scales."""
     C = backend.require_ext()
     dy, w = _prep(dy), _prep(w)
     dg, du = torch.empty_like(g), torch.empty_like(g)
     backend.count_launch()
-    C.gemm_glu(dy, w, None, dg, du, None, g, u, b_mn, ACT_CODES[act], None, None, None, row_counts, *_glu_extra(kw))
+    C.gemm_glu(dy, w, None, dg, du, None, g, u, b_mn, ACT_CODES[act], scale_a, scale_b, None, row_counts, *_glu_extra(kw))
     return dg, du
 
 
@@ -358,6 +451,7 @@ class FusedGLUFFN(torch.autograd.Function):
                                out_dtype=x.dtype)
             hq, sh = quantize_rows(h)
             y = raw_gemm(hq, q3, out_dtype=x.dtype, scale_a=sh, scale_b=s3)
+            ctx.fp8 = True
         else:
             h, g, u = glu_gemm(x, w1, w2, b_mn=True, act=act, save_pre=need_grad)
             y = raw_gemm(h, w3, b_mn=True)
@@ -370,12 +464,23 @@ class FusedGLUFFN(torch.autograd.Function):
     def backward(ctx: Any, dy: torch.Tensor):
         x, w1, w2, w3, g, u, h = ctx.saved_tensors
         dy = dy if _ok_stride(dy) else dy.contiguous()
-        dg, du = glu_gemm_bwd(dy, w3, g, u, b_mn=False, act=ctx.act)        # dh = dy @ W3^T (W3 [H,Mout] is "nk" here)
+        if getattr(ctx, 'fp8', False):
+            # e4m3 data-gradient GEMMs: dh = dy @ W3^T uses W3 as stored ([H, Mout] is K-major for it), dx uses W1 / W2 as stored
+            dyq, sdy = quantize_rows(dy)
+            q3, s3 = fp8_operand(w3, transpose=False)
+            dg, du = glu_gemm_bwd(dyq, q3, g, u, b_mn=False, act=ctx.act, scale_a=sdy, scale_b=s3)
+        else:
+            dg, du = glu_gemm_bwd(dy, w3, g, u, b_mn=False, act=ctx.act)    # dh = dy @ W3^T (W3 [H,Mout] is "nk" here)
         dw3 = raw_gemm(h, dy, a_mn=True, b_mn=True) if ctx.needs_input_grad[3] else None   # [H,Mout] = h^T @ dy
         dw1 = raw_gemm(x, dg, a_mn=True, b_mn=True) if ctx.needs_input_grad[1] else None   # [M,H] = x^T @ dg
         dw2 = raw_gemm(x, du, a_mn=True, b_mn=True) if ctx.needs_input_grad[2] else None
         dx = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and getattr(ctx, 'fp8', False):
+            (dgq, sg), (duq, su) = quantize_rows(dg), quantize_rows(du)
+            (q1, s1), (q2, s2) = fp8_operand(w1, transpose=False), fp8_operand(w2, transpose=False)   # [M, H]: K-major here
+            dx = raw_gemm(dgq, q1, out_dtype=dy.dtype, scale_a=sg, scale_b=s1)
+            dx = raw_gemm(duq, q2, epilogue=EPI_ADD, aux=dx, out_dtype=dy.dtype, scale_a=su, scale_b=s2)
+        elif ctx.needs_input_grad[0]:
             dx = raw_gemm(dg, w1)                                            # [T,M] = dg @ W1^T
             dx = raw_gemm(du, w2, epilogue=EPI_ADD, aux=dx)                  # += du @ W2^T (add fused in the epilogue)
         return dx, dw1, dw2, dw3, None, None

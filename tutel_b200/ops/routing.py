@@ -137,7 +137,7 @@ def _capacity(num_samples, num_global_experts, top_k, top_k_original, capacity_f
 
 
 def fused_extract_critical(logits: torch.Tensor, top_k: int, capacity_factor: float = 1.0, normalize_gate: bool = True,
-                           alignment: int = 1, group=None, inequivalent_tokens: bool = False):
+                           alignment: int = 1, group=None, inequivalent_tokens: bool = False, rows_bound: int = 0):
     """CUDA fast path of :func:`extract_critical` for GShard-loss top-k gates: softmax, top-k, gate normalisation, the
     auxiliary loss, queue locations, counts and the inverse slot map come out of TWO kernel launches
     (:func:`tutel_b200.ops.gating.fused_gate_route`); with a positive capacity factor nothing touches the host."""
@@ -146,11 +146,19 @@ def fused_extract_critical(logits: torch.Tensor, top_k: int, capacity_factor: fl
     top_k_original, top_k = top_k, min(top_k, E)
     num_samples = _num_samples(int(logits.size(0)), logits.device, group, inequivalent_tokens)
     static_cap = _capacity(num_samples, E, top_k, top_k_original, capacity_factor, None, group, alignment) if capacity_factor > 0 else 0
+    if capacity_factor <= 0 and rows_bound > 0:
+        # Dropless without the host round trip (the reference reads the fullest expert's count back, tutel/impls/
+        # fast_dispatch.py:192-193): a token never picks an expert twice, so `num_samples` rows per expert always suffice.
+        # The buffers are sized for that bound and every kernel downstream skips rows past the device-side counts.
+        static_cap = rows_bound if capacity_factor == 0 else min(rows_bound, top_k * int(-capacity_factor * ((num_samples + E - 1) // E)))
+        static_cap = (static_cap + alignment - 1) // alignment * alignment
+        capacity_factor = 1.0          # (only selects the "capacity is already known" branch below)
     idx, loc, gates, l_aux, counts, _top1, slot = fused_gate_route(logits, top_k, normalize_gate, static_cap)
     capacity = static_cap if capacity_factor > 0 else \
         _capacity(num_samples, E, top_k, top_k_original, capacity_factor, counts, group, alignment)
     crit = CriticalData(E, idx, loc, gates, capacity, counts)
     crit._slot_src = slot
+    crit.skip_padding = rows_bound > 0 and slot is not None     # bound-sized buffers: only rows below the counts are ever read
     return crit, l_aux
 
 

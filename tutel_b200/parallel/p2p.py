@@ -213,9 +213,12 @@ class P2PTransport:
             # fault injection (tests of the bounded-wait diagnostics): this rank "dies" for one collective - it neither
             # announces a receive buffer nor pushes, so the peers' kernels hit their spin timeout and report it
             return torch.zeros(list(out_shape), dtype=src.dtype, device=src.device)
+        side = slot != 0 and slot == getattr(self, '_side_slot', None)
+        blocks = self._blocks_per_peer(max(nbytes))
+        if side:    # runs next to an expert GEMM: 128-thread blocks that co-reside with its CTAs, more of them instead
+            blocks = min(4 * blocks, max(8, 1184 // self.world))
         return self._C.p2p_collective(self.heap, src, src_off, dst_off, nbytes, list(out_shape), 512 * slot,
-                                      self._next_epoch(slot), self._blocks_per_peer(max(nbytes)), self.stage_off,
-                                      self.bounce_bytes)
+                                      self._next_epoch(slot), blocks, self.stage_off, self.bounce_bytes, side)
 
     # ---- generic collectives (staging region; results are copied out so that callers may keep them) -------------
     def fits(self, nbytes: int) -> bool:
