@@ -6,8 +6,8 @@
 # Only the small functional cases run here (the sanitizer slows kernels down 10-100x); summaries land in gpurun_out/sanitizer/.
 OUT=gpurun_out/sanitizer
 mkdir -p $OUT
-for TOOL in memcheck racecheck synccheck initcheck; do
-  timeout 900 compute-sanitizer --tool $TOOL --print-limit 20 --error-exitcode 1 \
+for TOOL in ${TOOLS:-memcheck racecheck synccheck initcheck}; do
+  timeout ${TOOL_TIMEOUT:-420} compute-sanitizer --tool $TOOL --print-limit 20 --error-exitcode 1 \
       python bench/kernel_check.py --no_perf --inline --out $OUT/kernel_check_$TOOL.json > $OUT/$TOOL.log 2>&1
   echo "$TOOL rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $OUT/$TOOL.log | tail -1)"
 done

@@ -138,7 +138,7 @@ cudaError_t launch(const void* x, const void* w, const void* bias, void* y, cons
 // bias).  Every byte of an ACTIVE expert's weights is read exactly once with 16-byte loads and several loads in flight
 // per lane; experts without tokens cost one block exit.  No host synchronisation: counts are read on the device.
 constexpr int kHS = 64;         // hidden units per block
-constexpr int kFfnRows = 8;     // rows per pass (more rows re-stream the slice)
+constexpr int kFfnRows = 4;     // rows per pass (more rows re-stream the slice); keeps the kernel at <= 128 registers, 2 blocks / SM
 
 template <typename T> struct WVec;
 template <> struct WVec<float> {
@@ -181,8 +181,100 @@ __device__ __forceinline__ float ffn_act(float v, int act) {
   return v;
 }
 
+// One pass over this block's weight slices for ROWS (compile-time) rows: the inner products cost ROWS shared-memory reads
+// and 4*ROWS FMAs per 16 bytes of weights, so the common 1-2 rows per expert stay far below the issue limits.
+template <typename T, int ROWS>
+__device__ __forceinline__ void ffn_pass(const float* __restrict__ xs, float* __restrict__ hsm, const T* __restrict__ w1g,
+                                         const T* __restrict__ b1g, const T* __restrict__ w2g, const T* __restrict__ b2g,
+                                         float* __restrict__ yrow0, int nr, int K, int hs, int N, int act, bool add_bias) {
+  constexpr int V = WVec<T>::N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- layer 1: one hidden unit per warp and pass, lanes stride K with 16-byte loads ----
+  for (int j = warp; j < hs; j += 8) {
+    const T* wrow = w1g + static_cast<long long>(j) * K;
+    float acc[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = 0.0f;
+    for (int k = lane * V; k < K; k += 32 * V * 4) {
+      float wv[4][V];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kk = k + u * 32 * V;
+        if (kk < K) WVec<T>::load(wrow + kk, wv[u]);
+        else {
+#pragma unroll
+          for (int q = 0; q < V; ++q) wv[u][q] = 0.0f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kk = k + u * 32 * V;
+        if (kk < K) {
+#pragma unroll
+          for (int r = 0; r < ROWS; ++r) {
+            const float* xr = xs + r * K + kk;
+#pragma unroll
+            for (int q = 0; q < V; ++q) acc[r] = fmaf(xr[q], wv[u][q], acc[r]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+    if (lane == 0) {
+      const float b = b1g != nullptr ? ldf<T>(b1g + j) : 0.0f;
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) hsm[r * kHS + j] = ffn_act(acc[r] + b, act);
+    }
+  }
+  __syncthreads();
+  // ---- layer 2: each thread owns V output columns per pass and walks the slice's rows of W2 ----
+  for (int n = threadIdx.x * V; n < N; n += 256 * V) {
+    float acc[ROWS][V];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int q = 0; q < V; ++q) acc[r][q] = 0.0f;
+    for (int j = 0; j < hs; j += 8) {
+      float wv[8][V];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (j + u < hs) WVec<T>::load(w2g + static_cast<long long>(j + u) * N + n, wv[u]);
+        else {
+#pragma unroll
+          for (int q = 0; q < V; ++q) wv[u][q] = 0.0f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (j + u < hs) {
+#pragma unroll
+          for (int r = 0; r < ROWS; ++r) {
+            const float hv = hsm[r * kHS + j + u];
+#pragma unroll
+            for (int q = 0; q < V; ++q) acc[r][q] = fmaf(hv, wv[u][q], acc[r][q]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      if (r < nr) {
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+          float v = acc[r][q];
+          if (add_bias) v += ldf<T>(b2g + n + q);
+          atomicAdd(yrow0 + static_cast<long long>(r) * N + n + q, v);
+        }
+      }
+    }
+  }
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 skinny_ffn_kernel(const T* __restrict__ x, const T* __restrict__ w1, const T* __restrict__ b1, const T* __restrict__ w2,
                   const T* __restrict__ b2, float* __restrict__ y, const int* __restrict__ counts, int rows_cap, int K,
                   int H, int N, int act) {
@@ -195,105 +287,32 @@ skinny_ffn_kernel(const T* __restrict__ x, const T* __restrict__ w1, const T* __
   const int hs = min(kHS, H - h0);
   float* xs = sm;
   float* hsm = sm + kFfnRows * K;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const T* xg = x + static_cast<long long>(g) * rows_cap * K;
   const T* w1g = w1 + (static_cast<long long>(g) * H + h0) * K;
   const T* w2g = w2 + (static_cast<long long>(g) * H + h0) * N;
+  const T* b1g = b1 != nullptr ? b1 + static_cast<long long>(g) * H + h0 : nullptr;
+  const T* b2g = b2 != nullptr ? b2 + static_cast<long long>(g) * N : nullptr;
   float* yg = y + static_cast<long long>(g) * rows_cap * N;
+  const bool add_bias = blockIdx.x == 0 && b2 != nullptr;
 
   for (int r0 = 0; r0 < count; r0 += kFfnRows) {
     const int nr = min(kFfnRows, count - r0);
     __syncthreads();
-    for (int i = threadIdx.x * V; i < kFfnRows * K; i += 256 * V) {
+    for (int i = threadIdx.x * V; i < nr * K; i += 256 * V) {
       const int r = i / K, k = i - r * K;
       float f[V];
-      if (r < nr) WVec<T>::load(xg + static_cast<long long>(r0 + r) * K + k, f);
-      else {
-#pragma unroll
-        for (int q = 0; q < V; ++q) f[q] = 0.0f;
-      }
+      WVec<T>::load(xg + static_cast<long long>(r0 + r) * K + k, f);
 #pragma unroll
       for (int q = 0; q < V; ++q) xs[i + q] = f[q];
     }
     __syncthreads();
-    // ---- layer 1: one hidden unit per warp and pass, lanes stride K with 16-byte loads ----
-    for (int j = warp; j < hs; j += 8) {
-      const T* wrow = w1g + static_cast<long long>(j) * K;
-      float acc[kFfnRows];
-#pragma unroll
-      for (int r = 0; r < kFfnRows; ++r) acc[r] = 0.0f;
-      for (int k = lane * V; k < K; k += 32 * V * 4) {
-        float wv[4][V];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int kk = k + u * 32 * V;
-          if (kk < K) WVec<T>::load(wrow + kk, wv[u]);
-          else {
-#pragma unroll
-            for (int q = 0; q < V; ++q) wv[u][q] = 0.0f;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int kk = k + u * 32 * V;
-          if (kk < K) {
-#pragma unroll
-            for (int r = 0; r < kFfnRows; ++r) {
-              const float* xr = xs + r * K + kk;
-#pragma unroll
-              for (int q = 0; q < V; ++q) acc[r] = fmaf(xr[q], wv[u][q], acc[r]);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < kFfnRows; ++r)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
-      if (lane == 0) {
-        const float b = b1 != nullptr ? ldf<T>(b1 + static_cast<long long>(g) * H + h0 + j) : 0.0f;
-#pragma unroll
-        for (int r = 0; r < kFfnRows; ++r) hsm[r * kHS + j] = ffn_act(acc[r] + b, act);
-      }
-    }
-    __syncthreads();
-    // ---- layer 2: each thread owns V output columns per pass and walks the slice's rows of W2 ----
-    for (int n = threadIdx.x * V; n < N; n += 256 * V) {
-      float acc[kFfnRows][V];
-#pragma unroll
-      for (int r = 0; r < kFfnRows; ++r)
-#pragma unroll
-        for (int q = 0; q < V; ++q) acc[r][q] = 0.0f;
-      for (int j = 0; j < hs; j += 8) {
-        float wv[8][V];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (j + u < hs) WVec<T>::load(w2g + static_cast<long long>(j + u) * N + n, wv[u]);
-          else {
-#pragma unroll
-            for (int q = 0; q < V; ++q) wv[u][q] = 0.0f;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (j + u < hs) {
-#pragma unroll
-            for (int r = 0; r < kFfnRows; ++r) {
-              const float hv = hsm[r * kHS + j + u];
-#pragma unroll
-              for (int q = 0; q < V; ++q) acc[r][q] = fmaf(hv, wv[u][q], acc[r][q]);
-            }
-          }
-        }
-      }
-      for (int r = 0; r < nr; ++r) {
-#pragma unroll
-        for (int q = 0; q < V; ++q) {
-          float v = acc[r][q];
-          if (blockIdx.x == 0 && b2 != nullptr) v += ldf<T>(b2 + static_cast<long long>(g) * N + n + q);
-          atomicAdd(yg + static_cast<long long>(r0 + r) * N + n + q, v);
-        }
-      }
+    float* yrow0 = yg + static_cast<long long>(r0) * N;
+    if (nr == 1) ffn_pass<T, 1>(xs, hsm, w1g, b1g, w2g, b2g, yrow0, nr, K, hs, N, act, add_bias);
+    else if (nr == 2) ffn_pass<T, 2>(xs, hsm, w1g, b1g, w2g, b2g, yrow0, nr, K, hs, N, act, add_bias);
+    else {
+      for (int i = threadIdx.x + nr * K; i < kFfnRows * K; i += 256) xs[i] = 0.0f;       // rows [nr, 4) of the staged block
+      __syncthreads();
+      ffn_pass<T, kFfnRows>(xs, hsm, w1g, b1g, w2g, b2g, yrow0, nr, K, hs, N, act, add_bias);
     }
   }
 }

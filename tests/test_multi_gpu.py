@@ -40,6 +40,11 @@ def test_fused_engine_matches_fp32_torch_oracle():
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason='needs 2 GPUs')
+def test_fp8_experts_in_the_fused_engine():
+    _run('fp8', 2)
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason='needs 2 GPUs')
 def test_deep_stack_shares_one_buffer_ring():
     _run('deep', 2)
 

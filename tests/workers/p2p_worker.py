@@ -90,7 +90,7 @@ def test_collectives(env):
 
 
 def run_layer(env, fused, dtype, nle, steps=3, overlap=1, model_dim=256, hidden=512, tokens=512, expert='ffn', act=None,
-              is_postscore=True, output_dim=None, parallel_type='adaptive:1', same_experts=False):
+              is_postscore=True, output_dim=None, parallel_type='adaptive:1', same_experts=False, fp8=False):
     os.environ['TUTEL_B200_FUSED'] = '1' if fused else '0'
     r, dev = env.global_rank, env.local_device
     torch.manual_seed(7)
@@ -98,6 +98,8 @@ def run_layer(env, fused, dtype, nle, steps=3, overlap=1, model_dim=256, hidden=
                'activation_fn': act or (lambda t: F.relu(t))}
     if output_dim is not None:
         experts['output_dim'] = output_dim
+    if fp8:
+        experts['fp8'] = True
     layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2, 'capacity_factor': 1.5}, model_dim=model_dim, experts=experts,
                           seeds=(1, 1 if same_experts else r + 1, 1), a2a_ffn_overlap_degree=overlap, is_postscore=is_postscore,
                           parallel_type=parallel_type).to(dev).to(dtype)
@@ -205,6 +207,23 @@ def test_2dh(env):
     for tag, o in (('2dh d=1', outs[1]), ('2dh d=2 (async phases)', outs[2])):
         check('layer %s == flat' % tag, all(torch.allclose(a, b, atol=1e-5, rtol=1e-4) for a, b in zip(o, outs[0])))
     os.environ['TUTEL_B200_FUSED'] = '1'
+
+
+def test_fp8(env):
+    """e4m3 experts inside the fused engine (rows quantised in the push, fp8 forward + data-gradient GEMMs, weights quantised
+    once per step): same results as the unfused fp8 path, and a loss curve that tracks the bf16 run."""
+    for expert, act in (('ffn', None), ('llama_ffn', F.silu)):
+        a = run_layer(env, True, torch.bfloat16, 2, expert=expert, act=act, fp8=True, steps=6)
+        b = run_layer(env, False, torch.bfloat16, 2, expert=expert, act=act, fp8=True, steps=6)
+        c = run_layer(env, True, torch.bfloat16, 2, expert=expert, act=act, fp8=False, steps=6)
+        ok = all(abs(u - v) <= 3e-2 * max(1.0, abs(v)) for u, v in zip(a[0], b[0]))
+        ok = ok and torch.allclose(a[2], b[2], atol=6e-2, rtol=6e-2) and torch.allclose(a[1], b[1], atol=6e-2, rtol=1e-1)
+        if not ok:
+            print('fp8', expert, a[0], b[0], (a[2] - b[2]).abs().max().item(), (a[1] - b[1]).abs().max().item(), flush=True)
+        check('fused fp8 == unfused fp8 (%s)' % expert, ok)
+        drift = max(abs(u - v) / max(1e-6, abs(v)) for u, v in zip(a[0], c[0]))
+        print('[rank %d] fp8 vs bf16 losses (%s): %s vs %s (max rel. diff %.4f)' % (env.global_rank, expert, a[0], c[0], drift), flush=True)
+        check('fp8 loss curve within 5%% of bf16 (%s)' % expert, drift < 5e-2)
 
 
 def test_deep_stack(env):
@@ -331,6 +350,8 @@ def main():
         test_oracle(env)
     if which in ('all', 'deep'):
         test_deep_stack(env)
+    if which in ('all', 'fp8'):
+        test_fp8(env)
     if which in ('all', 'equiv'):
         test_parallel_equivalence(env)
     if which in ('sub',) or (which == 'all' and env.global_size >= 4):

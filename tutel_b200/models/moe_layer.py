@@ -108,7 +108,10 @@ class MOELayer(torch.nn.Module):
 
     @property
     def num_global_experts(self):
-        return int(self._num_global_experts)
+        # The count also lives in the `_num_global_experts` buffer (state-dict compatibility with the reference, which reads
+        # it back with int() - a device-to-host synchronisation in every forward once the module is on a GPU).  The Python
+        # copy is what the hot path uses: no synchronisation, and forward passes can be captured in CUDA graphs.
+        return self._n_global_experts
 
     # -------------------------------------------------------------------------------------------- construction
     def __init__(self, gate_type, model_dim: int, experts=None, scan_expert_func=None, result_func=None, group=None,
@@ -136,7 +139,8 @@ class MOELayer(torch.nn.Module):
         self.num_local_experts = local if local is not None else (local2 if local2 is not None else 1)
         if self.num_local_experts == -1:
             self.num_local_experts = 1
-        self.register_buffer('_num_global_experts', torch.tensor(MOELayer.global_expert_count(self.num_local_experts, self.group)))
+        self._n_global_experts = int(MOELayer.global_expert_count(self.num_local_experts, self.group))
+        self.register_buffer('_num_global_experts', torch.tensor(self._n_global_experts))
         if self.num_global_experts < self.world_size:
             self.sharded_count = self.world_size // self.num_global_experts
             self.num_local_experts = 1

@@ -261,7 +261,7 @@ def can_use_skinny_ffn(x: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, act_
     """Both expert layers in one weight-streaming launch (csrc/skinny_gemm.cu: skinny_ffn_kernel)."""
     v = 16 // x.element_size()
     return (can_use_skinny(x, w1) and act_kind in _SKINNY_ACTS and w1.dtype == w2.dtype and w1.size(2) == x.size(2) and
-            w2.size(1) == w1.size(1) and x.size(2) % v == 0 and w2.size(2) % v == 0 and 32 * x.size(2) + 2048 <= 200 * 1024)
+            w2.size(1) == w1.size(1) and x.size(2) % v == 0 and w2.size(2) % v == 0 and 16 * x.size(2) + 1024 <= 100 * 1024)
 
 
 def skinny_ffn(x, w1, b1, w2, b2, row_counts, act_kind):

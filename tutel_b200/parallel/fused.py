@@ -125,14 +125,15 @@ class _Lease:
     """What a forward leaves behind for its backward: the received rows (IN) and the combined rows (OUT).  They stay in
     the arena until the ring needs the set again (then they are copied out) or the backward has run."""
 
-    def __init__(self, bufs: _BufferSet, x_recv: Optional[torch.Tensor], y_comb: Optional[torch.Tensor]):
+    def __init__(self, bufs: _BufferSet, x_recv: Optional[torch.Tensor], y_comb: Optional[torch.Tensor], own_x: bool = False):
         self.bufs, self.x_recv, self.y_comb = bufs, x_recv, y_comb
+        self.own_x = own_x             # x_recv is already an ordinary tensor (fp8 path: the de-quantised copy of the rows)
         self.spill_event = None
 
     def spill(self, stream: torch.cuda.Stream):
         stream.wait_stream(torch.cuda.current_stream())      # the rows were completed by work queued on the main stream
         with torch.cuda.stream(stream):
-            if self.x_recv is not None:
+            if self.x_recv is not None and not self.own_x:
                 self.x_recv = self.x_recv.clone()
             if self.y_comb is not None:
                 self.y_comb = self.y_comb.clone()
@@ -293,6 +294,41 @@ class _Txn:
                 tns.record_stream(eng.side)
         return ev
 
+    def push_fp8(self, src: torch.Tensor, gates_f32: Optional[torch.Tensor], width: int) -> torch.cuda.Event:
+        """The same scatter-and-send with per-row e4m3 quantisation: rows of `width` bytes + one fp32 scale per row (half the
+        NVLink bytes of the 16-bit push)."""
+        g, eng, t, b = self.geo, self.eng, self.eng.t, self.bufs
+        soff = self._scale_off(width)
+        dst = [t.base_ptr(e // g.El) + b.off_in + ((e % g.El) * g.W + g.rank) * g.C * width for e in range(g.E)]
+        scl = [t.base_ptr(e // g.El) + b.off_in + soff + ((e % g.El) * g.W + g.rank) * g.C * 4 for e in range(g.E)]
+        dst_tab, scl_tab = self._table(('pd8', width), dst), self._table(('psc8', width), scl)
+        _, sig_tab = self._push_tables(width)
+        cur = torch.cuda.current_stream()
+        eng.side.wait_stream(cur)
+        chunks_per_expert = -(-g.C // self.chunk)
+        with torch.cuda.stream(eng.side):
+            backend.count_launch()
+            backend.require_ext().encode_rows_fp8(src, gates_f32, self.plan.slot_src, g.real_k, g.E, g.C, dst_tab, scl_tab, sig_tab,
+                                                  self.chunk, g.rank * g.El * chunks_per_expert, self.epoch,
+                                                  eng.chunk_counters(g.E).data_ptr())
+            ev = torch.cuda.Event()
+            ev.record(eng.side)
+        for tns in (src, self.plan.slot_src, gates_f32):
+            if tns is not None:
+                tns.record_stream(eng.side)
+        return ev
+
+    def _scale_off(self, width: int) -> int:
+        g = self.geo
+        return (g.G * g.C * width + 1023) // 1024 * 1024
+
+    def recv_view_fp8(self, width: int):
+        """(e4m3 rows [G, C, width], fp32 row scales [G, C]) of the IN buffer."""
+        g, t = self.geo, self.eng.t
+        q = t.view(self.bufs.off_in, [g.G, g.C, width], torch.float8_e4m3fn)
+        sc = t.view(self.bufs.off_in + self._scale_off(width), [g.G, g.C], torch.float32)
+        return q, sc
+
     def recv_view(self, width: int) -> torch.Tensor:
         g = self.geo
         return self.eng.t.view(self.bufs.off_in, [g.G, g.C, width], self.dtype)
@@ -355,15 +391,18 @@ def engine_for(layer, x: torch.Tensor, crit, d: int):
     if Sh > 1 and 1 < t.world < C_.get_world_size():
         r = Sh              # experts sharded inside a sub-group are always model-parallel (models/experts/ffn.py: materialize)
     if isinstance(ex, FusedExpertsNetwork):
-        if ex._act_kind not in G.FWD_EPILOGUE or ex.skip_expert or ex.fp8:
+        if ex._act_kind not in G.FWD_EPILOGUE or ex.skip_expert or (ex.fp8 and ex._act_kind != 'relu'):
+            return None
+        if ex.fp8 and (layer.model_dim % 16 or ex.hidden_size % 16 or ex.output_dim % 16):
             return None
         if ex.batched_fc1_w.dtype != x.dtype or (layer.model_dim % 8) or (ex.hidden_size % 8) or (ex.output_dim % 8):
             return None
         M, H, Mo = layer.model_dim, ex.hidden_size * (Sh // r if Sh > 1 else 1), ex.output_dim
     elif isinstance(ex, LlamaFFNNetwork):
-        if ex.fp8 or G.classify_activation(ex.activation_fn) not in G.ACT_CODES or ex.W_fc1.dtype != x.dtype:
+        if G.classify_activation(ex.activation_fn) not in G.ACT_CODES or ex.W_fc1.dtype != x.dtype:
             return None
-        if any(int(v) % 8 for v in ex.full_shapes['W_fc1'][1:]) or int(ex.full_shapes['W_fc3'][2]) % 8:
+        align = 16 if ex.fp8 else 8
+        if any(int(v) % align for v in ex.full_shapes['W_fc1'][1:]) or int(ex.full_shapes['W_fc3'][2]) % align:
             return None
         M, H, Mo = layer.model_dim, int(ex.full_shapes['W_fc1'][2]), int(ex.full_shapes['W_fc3'][2])
     else:
@@ -400,7 +439,7 @@ class _Runner:
             kplan = _virtual_plan(plan, layer.num_global_experts, layer.sharded_count, geo.copies)
         else:
             kplan = _Plan(plan.idx_ks, plan.loc_ks, plan.slot_src)
-        call = (self.eng, self.ring, geo, kplan, self.d, layer.is_postscore)
+        call = (self.eng, self.ring, geo, kplan, self.d, layer.is_postscore, bool(getattr(ex, 'fp8', False)))
         if hasattr(ex, 'full_shapes'):
             w1, w2, w3 = (ex._full(n, layer.group) for n in ('W_fc1', 'W_fc2', 'W_fc3'))
             return _FusedGLUMoE.apply(call, G.classify_activation(ex.activation_fn), x, gates, w1, w2, w3)
@@ -409,7 +448,7 @@ class _Runner:
 
 
 def _begin(call, dtype) -> _Txn:
-    eng, ring, geo, kplan, d, _ = call
+    eng, ring, geo, kplan, d = call[:5]
     return _Txn(eng, geo, kplan, ring.next(eng.side), d, dtype)
 
 
@@ -418,28 +457,50 @@ class _FusedMoE(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx: Any, call, act_kind: str, x, gates, w1, b1, w2, b2):
-        eng, ring, geo, kplan, d, is_postscore = call
+        eng, ring, geo, kplan, d, is_postscore, fp8 = call
         M, H, Mo = geo.M, geo.H, geo.Mo
         need_grad = any(ctx.needs_input_grad[2:])
         gates_f32 = gates.detach().to(torch.float32).contiguous()
         tx = _begin(call, x.dtype)
 
-        # (1) dispatch: tokens -> expert GPUs' IN buffers (communication stream, overlaps GEMM1)
-        ev = tx.push(x, None if is_postscore else gates_f32, M)
-
-        # (2) GEMM1 + bias + activation on rows as they arrive
-        x_recv = tx.recv_view(M)
-        cg, bn1, _ = eng.tile_counts(geo.C, H)
         b1v = None if b1 is None else b1.reshape(w1.size(0), -1)
-        pre = None
-        if act_kind != 'relu' and need_grad:
-            pre = torch.empty([geo.G, geo.C, H], dtype=x.dtype, device=x.device)
-        act = G.raw_gemm(x_recv, w1, epilogue=G.FWD_EPILOGUE[act_kind], bias=b1v, cta_group=cg, block_n=bn1, d2=pre,
-                         **tx.wait_kwargs())
-
-        # (3) GEMM2 + bias, epilogue writes into the source GPUs' OUT buffers and signals per expert
         b2v = None if b2 is None else b2.reshape(w2.size(0), -1)
-        G.raw_gemm(act, w2, b_mn=True, epilogue=G.EPI_BIAS if b2 is not None else G.EPI_NONE, bias=b2v, **tx.combine_kwargs(Mo))
+        cg, bn1, _ = eng.tile_counts(geo.C, H)
+        pre, x16_event = None, None
+        if fp8:
+            # e4m3 end to end: rows are quantised in the push (half the NVLink bytes), both GEMMs run at the fp8 rate on
+            # weight copies quantised once per optimizer step; scales are applied in the epilogues
+            ev = tx.push_fp8(x, None if is_postscore else gates_f32, M)
+            xq, sx = tx.recv_view_fp8(M)
+            w1q, s1 = G.fp8_operand(w1, transpose=False)
+            act = G.raw_gemm(xq, w1q, epilogue=G.EPI_BIAS_RELU, bias=b1v, out_dtype=x.dtype, scale_a=sx, scale_b=s1, cta_group=cg,
+                             block_n=bn1, **tx.wait_kwargs())
+            x_recv = None
+            if need_grad:       # the 16-bit weight-gradient GEMM needs the rows back in 16 bit: de-quantise next to GEMM2
+                eng.side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(eng.side):
+                    backend.count_launch()
+                    x_recv = backend.require_ext().dequant_rows(xq, sx, x.dtype)
+                    x16_event = torch.cuda.Event()
+                    x16_event.record(eng.side)
+            aq, sa = G.quantize_rows(act)
+            w2q, s2 = G.fp8_operand(w2, transpose=True)
+            G.raw_gemm(aq, w2q, epilogue=G.EPI_BIAS if b2 is not None else G.EPI_NONE, bias=b2v, scale_a=sa, scale_b=s2,
+                       **tx.combine_kwargs(Mo))
+        else:
+            # (1) dispatch: tokens -> expert GPUs' IN buffers (communication stream, overlaps GEMM1)
+            ev = tx.push(x, None if is_postscore else gates_f32, M)
+
+            # (2) GEMM1 + bias + activation on rows as they arrive
+            x_recv = tx.recv_view(M)
+            if act_kind != 'relu' and need_grad:
+                pre = torch.empty([geo.G, geo.C, H], dtype=x.dtype, device=x.device)
+            act = G.raw_gemm(x_recv, w1, epilogue=G.FWD_EPILOGUE[act_kind], bias=b1v, cta_group=cg, block_n=bn1, d2=pre,
+                             **tx.wait_kwargs())
+
+            # (3) GEMM2 + bias, epilogue writes into the source GPUs' OUT buffers and signals per expert
+            G.raw_gemm(act, w2, b_mn=True, epilogue=G.EPI_BIAS if b2 is not None else G.EPI_NONE, bias=b2v,
+                       **tx.combine_kwargs(Mo))
 
         # (4) combine: weighted sum of each token's k rows once their experts have delivered
         out = tx.decode(_virtual_gates(gates_f32, geo) if is_postscore else None, Mo)
@@ -448,7 +509,8 @@ class _FusedMoE(torch.autograd.Function):
         ctx.call, ctx.act_kind = call, act_kind
         ctx.has_b1, ctx.has_b2 = b1 is not None, b2 is not None
         if need_grad:
-            lease = _Lease(tx.bufs, x_recv, tx.comb_view(Mo) if is_postscore else None)
+            lease = _Lease(tx.bufs, x_recv, tx.comb_view(Mo) if is_postscore else None, own_x=fp8)
+            lease.spill_event = x16_event
             tx.bufs.holder = weakref.ref(lease)
             ctx.lease = lease
             ctx.save_for_backward(x, gates, w1, w2, act, pre)
@@ -457,7 +519,7 @@ class _FusedMoE(torch.autograd.Function):
     @staticmethod
     def backward(ctx: Any, dout: torch.Tensor):
         call, act_kind, lease = ctx.call, ctx.act_kind, ctx.lease
-        eng, ring, geo, kplan, d, is_postscore = call
+        eng, ring, geo, kplan, d, is_postscore, fp8 = call
         x, gates, w1, w2, act, pre = ctx.saved_tensors
         M, H, Mo, W, El, C = geo.M, geo.H, geo.Mo, geo.W, geo.El, geo.C
         dout = dout.contiguous()
@@ -472,25 +534,38 @@ class _FusedMoE(torch.autograd.Function):
 
         # (b) dispatch the output gradients to the expert GPUs (decode.bwd == encode of dout)
         tx = _begin(call, dout.dtype)
-        ev = tx.push(dout, gates_f32 if is_postscore else None, Mo)
-        dy_recv = tx.recv_view(Mo)
-
-        # (c) dh = (dy @ W2^T) * act'(.)   as rows arrive
         cg, bnh, _ = eng.tile_counts(C, H)
         want_db1 = ctx.has_b1 and ctx.needs_input_grad[5]
         db1_acc = torch.zeros([w1.size(0), H], dtype=torch.float32, device=dout.device) if want_db1 else None
-        if act_kind == 'relu':
-            dh = G.raw_gemm(dy_recv, w2, epilogue=G.EPI_RELU_BWD, aux=act, cta_group=cg, block_n=bnh, colsum=db1_acc,
-                            **tx.wait_kwargs())
-        else:
-            dh = G.raw_gemm(dy_recv, w2, epilogue=G.EPI_ACT_BWD, aux=pre, act=G.ACT_CODES[act_kind], cta_group=cg, block_n=bnh,
-                            colsum=db1_acc, **tx.wait_kwargs())
-
-        # (e) dX_e = dh @ W1, epilogue pushes into the source GPUs' OUT buffers.  Collective decision: every rank
-        #     must run it if any rank needs input gradients - the flag is part of the saved context (same program).
         need_dx = ctx.needs_input_grad[2] or (not is_postscore and ctx.needs_input_grad[3])
-        if need_dx:
-            G.raw_gemm(dh, w1, b_mn=True, **tx.combine_kwargs(M))
+        if fp8:
+            ev = tx.push_fp8(dout, gates_f32 if is_postscore else None, Mo)
+            dyq, sdy = tx.recv_view_fp8(Mo)
+            w2q, s2 = G.fp8_operand(w2, transpose=False)        # dh = dy @ W2^T: W2 [H, Mout] is K-major for this product
+            dh = G.raw_gemm(dyq, w2q, epilogue=G.EPI_RELU_BWD, aux=act, out_dtype=dout.dtype, scale_a=sdy, scale_b=s2,
+                            cta_group=cg, block_n=bnh, colsum=db1_acc, **tx.wait_kwargs())
+            if need_dx:
+                dhq, sdh = G.quantize_rows(dh)
+                w1q, s1 = G.fp8_operand(w1, transpose=True)     # dx = dh @ W1: W1^T [M, H] K-major
+                G.raw_gemm(dhq, w1q, scale_a=sdh, scale_b=s1, **tx.combine_kwargs(M))
+            backend.count_launch()
+            dy_recv = backend.require_ext().dequant_rows(dyq, sdy, dout.dtype)     # all rows have arrived (dh GEMM is queued before)
+        else:
+            ev = tx.push(dout, gates_f32 if is_postscore else None, Mo)
+            dy_recv = tx.recv_view(Mo)
+
+            # (c) dh = (dy @ W2^T) * act'(.)   as rows arrive
+            if act_kind == 'relu':
+                dh = G.raw_gemm(dy_recv, w2, epilogue=G.EPI_RELU_BWD, aux=act, cta_group=cg, block_n=bnh, colsum=db1_acc,
+                                **tx.wait_kwargs())
+            else:
+                dh = G.raw_gemm(dy_recv, w2, epilogue=G.EPI_ACT_BWD, aux=pre, act=G.ACT_CODES[act_kind], cta_group=cg, block_n=bnh,
+                                colsum=db1_acc, **tx.wait_kwargs())
+
+            # (e) dX_e = dh @ W1, epilogue pushes into the source GPUs' OUT buffers.  Collective decision: every rank
+            #     must run it if any rank needs input gradients - the flag is part of the saved context (same program).
+            if need_dx:
+                G.raw_gemm(dh, w1, b_mn=True, **tx.combine_kwargs(M))
 
         # (d, f) weight gradients over all W*C received rows of each local expert
         act_e, dh_e = act.view(El, W * C, H), dh.view(El, W * C, H)
@@ -517,21 +592,41 @@ class _FusedGLUMoE(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx: Any, call, act: str, x, gates, w1, w2, w3):
-        eng, ring, geo, kplan, d, is_postscore = call
+        eng, ring, geo, kplan, d, is_postscore, fp8 = call
         M, H, Mo = geo.M, geo.H, geo.Mo
         need_grad = any(ctx.needs_input_grad[2:])
         gates_f32 = gates.detach().to(torch.float32).contiguous()
         tx = _begin(call, x.dtype)
-        ev = tx.push(x, None if is_postscore else gates_f32, M)
-        x_recv = tx.recv_view(M)
         cg, _, _ = eng.tile_counts(geo.C, H)
-        h, g, u = G.glu_gemm(x_recv, w1, w2, b_mn=True, act=act, save_pre=need_grad, cta_group=cg, **tx.wait_kwargs())
-        G.raw_gemm(h, w3, b_mn=True, **tx.combine_kwargs(Mo))
+        x16_event = None
+        if fp8:
+            ev = tx.push_fp8(x, None if is_postscore else gates_f32, M)
+            xq, sx = tx.recv_view_fp8(M)
+            (q1, s1), (q2, s2) = G.fp8_operand(w1, transpose=True), G.fp8_operand(w2, transpose=True)      # [El, H, M] K-major
+            h, g, u = G.glu_gemm(xq, q1, q2, b_mn=False, act=act, save_pre=need_grad, scale_a=sx, scale_b=s1, scale_b2=s2,
+                                 out_dtype=x.dtype, cta_group=cg, **tx.wait_kwargs())
+            x_recv = None
+            if need_grad:
+                eng.side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(eng.side):
+                    backend.count_launch()
+                    x_recv = backend.require_ext().dequant_rows(xq, sx, x.dtype)
+                    x16_event = torch.cuda.Event()
+                    x16_event.record(eng.side)
+            hq, sh = G.quantize_rows(h)
+            q3, s3 = G.fp8_operand(w3, transpose=True)                                                        # [El, Mo, H]
+            G.raw_gemm(hq, q3, scale_a=sh, scale_b=s3, **tx.combine_kwargs(Mo))
+        else:
+            ev = tx.push(x, None if is_postscore else gates_f32, M)
+            x_recv = tx.recv_view(M)
+            h, g, u = G.glu_gemm(x_recv, w1, w2, b_mn=True, act=act, save_pre=need_grad, cta_group=cg, **tx.wait_kwargs())
+            G.raw_gemm(h, w3, b_mn=True, **tx.combine_kwargs(Mo))
         out = tx.decode(_virtual_gates(gates_f32, geo) if is_postscore else None, Mo)
         torch.cuda.current_stream().wait_event(ev)
         ctx.call, ctx.act = call, act
         if need_grad:
-            lease = _Lease(tx.bufs, x_recv, tx.comb_view(Mo) if is_postscore else None)
+            lease = _Lease(tx.bufs, x_recv, tx.comb_view(Mo) if is_postscore else None, own_x=fp8)
+            lease.spill_event = x16_event
             tx.bufs.holder = weakref.ref(lease)
             ctx.lease = lease
             ctx.save_for_backward(x, gates, w1, w2, w3, g, u, h)
@@ -540,7 +635,7 @@ class _FusedGLUMoE(torch.autograd.Function):
     @staticmethod
     def backward(ctx: Any, dout: torch.Tensor):
         call, act, lease = ctx.call, ctx.act, ctx.lease
-        eng, ring, geo, kplan, d, is_postscore = call
+        eng, ring, geo, kplan, d, is_postscore, fp8 = call
         x, gates, w1, w2, w3, g, u, h = ctx.saved_tensors
         M, H, Mo, W, El, C = geo.M, geo.H, geo.Mo, geo.W, geo.El, geo.C
         dout = dout.contiguous()
@@ -551,16 +646,31 @@ class _FusedGLUMoE(torch.autograd.Function):
         if is_postscore and ctx.needs_input_grad[3]:
             dgates = _gate_grad(dout, y_comb, kplan, geo).to(gates.dtype)
         tx = _begin(call, dout.dtype)
-        ev = tx.push(dout, gates_f32 if is_postscore else None, Mo)
-        dy_recv = tx.recv_view(Mo)
         cg, _, _ = eng.tile_counts(C, H)
-        # dh = dy @ W3^T stays in TMEM; the epilogue emits dg and du as the gradient rows arrive
-        dg, du = G.glu_gemm_bwd(dy_recv, w3, g, u, b_mn=False, act=act, cta_group=cg, **tx.wait_kwargs())
         need_dx = ctx.needs_input_grad[2] or (not is_postscore and ctx.needs_input_grad[3])
-        if need_dx:
-            ck = tx.combine_kwargs(M)
-            part = G.raw_gemm(dg, w1, b_group_div=W, cta_group=ck['cta_group'], block_n=ck['block_n'])   # dg @ W1^T (local)
-            G.raw_gemm(du, w2, epilogue=G.EPI_ADD, aux=part, **ck)
+        if fp8:
+            ev = tx.push_fp8(dout, gates_f32 if is_postscore else None, Mo)
+            dyq, sdy = tx.recv_view_fp8(Mo)
+            q3, s3 = G.fp8_operand(w3, transpose=False)          # dh = dy @ W3^T: W3 [H, Mo] is K-major for this product
+            dg, du = G.glu_gemm_bwd(dyq, q3, g, u, b_mn=False, act=act, scale_a=sdy, scale_b=s3, cta_group=cg, **tx.wait_kwargs())
+            if need_dx:
+                ck = tx.combine_kwargs(M)
+                (dgq, sg), (duq, su) = G.quantize_rows(dg), G.quantize_rows(du)
+                (q1, s1), (q2, s2) = G.fp8_operand(w1, transpose=False), G.fp8_operand(w2, transpose=False)   # [El, M, H]
+                part = G.raw_gemm(dgq, q1, out_dtype=dout.dtype, scale_a=sg, scale_b=s1, b_group_div=W, cta_group=ck['cta_group'],
+                                  block_n=ck['block_n'])
+                G.raw_gemm(duq, q2, epilogue=G.EPI_ADD, aux=part, scale_a=su, scale_b=s2, **ck)
+            backend.count_launch()
+            dy_recv = backend.require_ext().dequant_rows(dyq, sdy, dout.dtype)
+        else:
+            ev = tx.push(dout, gates_f32 if is_postscore else None, Mo)
+            dy_recv = tx.recv_view(Mo)
+            # dh = dy @ W3^T stays in TMEM; the epilogue emits dg and du as the gradient rows arrive
+            dg, du = G.glu_gemm_bwd(dy_recv, w3, g, u, b_mn=False, act=act, cta_group=cg, **tx.wait_kwargs())
+            if need_dx:
+                ck = tx.combine_kwargs(M)
+                part = G.raw_gemm(dg, w1, b_group_div=W, cta_group=ck['cta_group'], block_n=ck['block_n'])   # dg @ W1^T (local)
+                G.raw_gemm(du, w2, epilogue=G.EPI_ADD, aux=part, **ck)
         x_e, dy_e = x_recv.reshape(El, W * C, M), dy_recv.view(El, W * C, Mo)
         dw3 = G.raw_gemm(h.view(El, W * C, H), dy_e, a_mn=True, b_mn=True) if ctx.needs_input_grad[6] else None
         dw1 = G.raw_gemm(x_e, dg.view(El, W * C, H), a_mn=True, b_mn=True) if ctx.needs_input_grad[4] else None
