@@ -18,6 +18,7 @@ ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--experts', type=int, default=8)
 ap.add_argument('--expert_type', type=str, default='ffn')
 ap.add_argument('--overlap', type=int, default=1)
+ap.add_argument('--fp8', action='store_true')
 ap.add_argument('--reference', action='store_true', help='profile the unmodified reference (baseline/_ref) instead')
 args = ap.parse_args()
 if args.reference:
@@ -31,7 +32,7 @@ rank, world, dev = env.global_rank, env.global_size, env.local_device
 torch.set_default_dtype(torch.bfloat16)
 layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2, 'capacity_factor': 1.0}, model_dim=4096,
                       experts={'type': args.expert_type, 'num_experts_per_device': args.experts // world, 'hidden_size_per_expert': 14336,
-                               'activation_fn': lambda x: F.relu(x)},
+                               'activation_fn': lambda x: F.relu(x), **({'fp8': True} if args.fp8 else {})},
                       scan_expert_func=lambda n, p: setattr(p, 'skip_allreduce', True), seeds=(1, rank + 1, 1), a2a_ffn_overlap_degree=args.overlap).to(dev)
 opt = torch.optim.SGD(layer.parameters(), lr=1e-5)
 shared = [p for p in layer.parameters() if not hasattr(p, 'skip_allreduce')]

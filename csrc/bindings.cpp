@@ -374,6 +374,20 @@ std::vector<at::Tensor> quantize_rows(const at::Tensor& x) {
   return {q, scale};
 }
 
+// x [G, R, K] (16 bit) -> [qT e4m3 [G, K, R], scale fp32 [G, K]]   (transposed copy with one scale per output row)
+std::vector<at::Tensor> quantize_transpose(const at::Tensor& x) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && x.dim() == 3 && x.element_size() == 2 && x.size(1) % 128 == 0 && x.size(2) % 64 == 0,
+              "quantize_transpose: contiguous 16-bit CUDA tensor [G, R, K] with R % 128 == 0 and K % 64 == 0 expected");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int G = static_cast<int>(x.size(0)), R = static_cast<int>(x.size(1)), K = static_cast<int>(x.size(2));
+  at::Tensor q = at::empty({G, K, R}, x.options().dtype(at::kFloat8_e4m3fn));
+  at::Tensor scale = at::empty({G, K}, x.options().dtype(at::kFloat));
+  at::Tensor ws = at::empty({G, K}, x.options().dtype(at::kFloat));
+  TB_CHECK_CUDA(tb::quantize_transpose_e4m3(x.data_ptr(), q.data_ptr(), scale.data_ptr<float>(), ws.data_ptr<float>(), G, R, K,
+                                            elem_type_of(x), cur_stream()));
+  return {q, scale};
+}
+
 // q e4m3 [.., K], scale fp32 [..] -> 16-bit [.., K]
 at::Tensor dequant_rows(const at::Tensor& q, const at::Tensor& scale, at::ScalarType dtype) {
   TORCH_CHECK(q.is_cuda() && q.is_contiguous() && q.scalar_type() == at::kFloat8_e4m3fn && scale.is_cuda() && scale.is_contiguous() &&
@@ -539,6 +553,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("skinny_ffn", &skinny_ffn);
   m.def("quantize_rows", &quantize_rows);
   m.def("dequant_rows", &dequant_rows);
+  m.def("quantize_transpose", &quantize_transpose);
   register_symm_bindings(m);
   register_cpu_bindings(m);
   register_jit_bindings(m);

@@ -554,6 +554,80 @@ dequant_rows_kernel(const uint8_t* __restrict__ q, const float* __restrict__ sca
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// transposing e4m3 quantisation of a weight: x [G, R, K] (16 bit) -> qT [G, K, R] with one scale per OUTPUT row k
+// (= per column of x).  Two passes over x and half-size writes, instead of a 16-bit transpose copy followed by a row
+// quantisation: (1) column |max| with 16-byte loads, (2) 128 x 64 tiles through shared memory, coalesced on both sides.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+col_amax_kernel(const T* __restrict__ x, float* __restrict__ amax, int R, int K, int rows_per_split) {
+  __shared__ float sm[16][16 * 8 + 1];
+  const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int col = (blockIdx.x * 16 + cl) * 8;
+  const int g = blockIdx.z;
+  const int r_begin = blockIdx.y * rows_per_split;
+  const int r_end = min(R, r_begin + rows_per_split);
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 0.0f;
+  if (col < K) {
+    const T* base = x + static_cast<long long>(g) * R * K + col;
+    for (int r = r_begin + rl; r < r_end; r += 16) {
+      float f[8];
+      Vec<T>::unpack(ptx::ld_nc_v4(base + static_cast<long long>(r) * K), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fmaxf(a[i], fabsf(f[i]));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[rl][cl * 8 + i] = a[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 128; c += 256) {
+    float t = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) t = fmaxf(t, sm[q][c]);
+    const int n = blockIdx.x * 128 + c;
+    if (n < K) atomicMax(reinterpret_cast<int*>(amax) + static_cast<long long>(g) * K + n, __float_as_int(t));   // t >= 0
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+quantize_transpose_kernel(const T* __restrict__ x, const float* __restrict__ amax, uint8_t* __restrict__ qT,
+                          float* __restrict__ scale, int R, int K) {
+  // tile: rows [r0, r0+128) x columns [k0, k0+64)
+  __shared__ __align__(16) uint8_t sm_in[128 * 144];       // 16-bit tile, row stride 144 B
+  __shared__ uint32_t sm_out[64 * 33];                     // e4m3 tile transposed: [k][r/4] words, row stride 33 words
+  const int g = blockIdx.z;
+  const int r0 = blockIdx.y * 128, k0 = blockIdx.x * 64;
+  const T* xg = x + static_cast<long long>(g) * R * K;
+  for (int i = threadIdx.x; i < 128 * 8; i += 256) {
+    const int r = i >> 3, v = i & 7;
+    const uint4 u = ptx::ld_nc_v4(xg + static_cast<long long>(r0 + r) * K + k0 + v * 8);
+    *reinterpret_cast<uint4*>(sm_in + r * 144 + v * 16) = u;
+  }
+  const int k = threadIdx.x & 63;
+  const float am = amax[static_cast<long long>(g) * K + k0 + k];
+  const float sc = am > 0.0f ? am * (1.0f / 448.0f) : 1.0f;
+  const float inv = 1.0f / sc;
+  if (blockIdx.y == 0 && threadIdx.x < 64) scale[static_cast<long long>(g) * K + k0 + k] = sc;
+  __syncthreads();
+  for (int r4 = threadIdx.x >> 6; r4 < 32; r4 += 4) {
+    float f[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f[j] = to_f<T>(*reinterpret_cast<const T*>(sm_in + (r4 * 4 + j) * 144 + k * 2)) * inv;
+    const __nv_fp8x4_e4m3 p4(make_float4(f[0], f[1], f[2], f[3]));
+    sm_out[k * 33 + r4] = *reinterpret_cast<const uint32_t*>(&p4);
+  }
+  __syncthreads();
+  uint8_t* og = qT + static_cast<long long>(g) * K * R;
+  for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+    const int kk = i >> 5, w = i & 31;
+    *reinterpret_cast<uint32_t*>(og + static_cast<long long>(k0 + kk) * R + r0 + w * 4) = sm_out[kk * 33 + w];
+  }
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -672,6 +746,31 @@ cudaError_t dequant_rows_e4m3(const void* q, const float* scale, void* y, long l
     dequant_rows_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const uint8_t*>(q), scale, static_cast<__half*>(y), R, K);
   else
     return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t quantize_transpose_e4m3(const void* x, void* qT, float* scale, float* amax_ws, int G, int R, int K, int elem_type,
+                                    cudaStream_t stream) {
+  if (G <= 0 || R <= 0 || K <= 0) return cudaSuccess;
+  if (R % 128 || K % 64 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(qT) & 3)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(amax_ws, 0, sizeof(float) * static_cast<size_t>(G) * K, stream);
+  if (e != cudaSuccess) return e;
+  const int strips = (K + 127) / 128;
+  int splits = 1;
+  while (static_cast<long long>(strips) * G * splits < 2LL * num_sms() && R / (splits * 2) >= 64) splits *= 2;
+  const int rps = (R + splits - 1) / splits;
+  dim3 g1(strips, splits, G), g2(K / 64, R / 128, G);
+  if (elem_type == ET_BF16) {
+    col_amax_kernel<__nv_bfloat16><<<g1, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), amax_ws, R, K, rps);
+    quantize_transpose_kernel<__nv_bfloat16><<<g2, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), amax_ws,
+                                                                     static_cast<uint8_t*>(qT), scale, R, K);
+  } else if (elem_type == ET_F16) {
+    col_amax_kernel<__half><<<g1, 256, 0, stream>>>(static_cast<const __half*>(x), amax_ws, R, K, rps);
+    quantize_transpose_kernel<__half><<<g2, 256, 0, stream>>>(static_cast<const __half*>(x), amax_ws, static_cast<uint8_t*>(qT),
+                                                              scale, R, K);
+  } else {
+    return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 

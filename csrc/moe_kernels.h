@@ -86,6 +86,11 @@ cudaError_t set_spin_timeout_gemm(unsigned long long ns);
 cudaError_t quantize_rows_e4m3(const void* x, void* q, float* scale, long long R, int K, int elem_type,
                                cudaStream_t stream);
 
+// qT[g, k, r] = e4m3(x[g, r, k] / scale[g, k]),  scale[g, k] = max_r |x[g, r, k]| / 448: the transposed, row-scaled copy of a
+// 16-bit weight (R % 128 == 0, K % 64 == 0).  amax_ws: fp32 [G, K] workspace.
+cudaError_t quantize_transpose_e4m3(const void* x, void* qT, float* scale, float* amax_ws, int G, int R, int K, int elem_type,
+                                    cudaStream_t stream);
+
 // y[r, :] = q[r, :] * scale[r]  (e4m3 -> fp16 / bf16), K % 16 == 0
 cudaError_t dequant_rows_e4m3(const void* q, const float* scale, void* y, long long R, int K, int elem_type,
                               cudaStream_t stream);

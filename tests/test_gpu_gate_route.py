@@ -201,3 +201,13 @@ def test_graphed_dropless_forward_matches_eager():
             want = layer(x, megablocks_size=1)
         got = fast(x).clone()
         assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)
+
+
+def test_quantize_transpose_matches_row_quantisation_of_the_transpose(C):
+    """Transposing e4m3 quantisation of a weight == row quantisation of its 16-bit transpose (same scales, same bytes)."""
+    torch.manual_seed(13)
+    w = (torch.randn(3, 256, 192, device='cuda') * 0.3).bfloat16()
+    qT, sT = C.quantize_transpose(w)
+    q, s = C.quantize_rows(w.transpose(1, 2).contiguous())
+    assert qT.shape == (3, 192, 256) and torch.allclose(sT, s, rtol=1e-6)
+    assert torch.equal(qT.view(torch.uint8), q.view(torch.uint8))

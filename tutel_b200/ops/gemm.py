@@ -326,8 +326,12 @@ def fp8_operand(w: torch.Tensor, transpose: bool):
     hit = _FP8_WEIGHT_CACHE.get(key)
     if hit is not None and hit[0] == stamp and hit[3]() is anchor:
         return hit[1], hit[2]
-    src = w.detach().transpose(1, 2) if transpose else w.detach()
-    q, s = quantize_rows(src.contiguous())
+    src = w.detach()
+    if transpose and src.dim() == 3 and src.is_contiguous() and src.element_size() == 2 and src.size(1) % 128 == 0 and src.size(2) % 64 == 0:
+        backend.count_launch(2)        # column |max| + transposing quantisation: no 16-bit transpose copy
+        q, s = backend.require_ext().quantize_transpose(src)
+    else:
+        q, s = quantize_rows((src.transpose(1, 2) if transpose else src).contiguous())
     if len(_FP8_WEIGHT_CACHE) > 256:
         for k in [k for k, v in _FP8_WEIGHT_CACHE.items() if v[3]() is None]:
             del _FP8_WEIGHT_CACHE[k]
