@@ -12,6 +12,7 @@ model_dim 4096, hidden 14336, 16 x 512 = 8192 tokens per GPU, capacity_factor 1.
 Prints one JSON line on rank 0.
 """
 import argparse
+import gc
 import json
 import os
 import sys
@@ -163,6 +164,10 @@ def main():
         prev_blk = blk
     if args.impl == 'ours':
         launches0 = backend.launch_count()
+    # (both arms) no cyclic-garbage collection inside a timed region: with tightly coupled ranks one collector pause on any
+    # rank stalls every rank
+    gc.collect()
+    gc.disable()
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -171,6 +176,7 @@ def main():
     e1.record()
     sync()
     t_wall1 = time.time()
+    gc.enable()
     ms = maxreduce(e0.elapsed_time(e1))
     launches = (backend.launch_count() - launches0) if args.impl == 'ours' else None
     clocks = None
@@ -213,11 +219,14 @@ def main():
             ev.record()
         run(3)
         sync()
+        gc.collect()
+        gc.disable()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         last = run(args.steps)
         f1.record()
         sync()
+        gc.enable()
         ms_e2e = maxreduce(f0.elapsed_time(f1))
         e2e = {'value': world * BATCH * TOKENS * args.steps / (ms_e2e * 1e-3), 'unit': 'tokens/s',
                'h2d_bytes_per_step': x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size(),

@@ -190,3 +190,40 @@ def test_layer_with_fused_gate_matches_default_path(monkeypatch):
         a, b = run(True, bpr), run(False, bpr)
         for u, v in zip(a, b):
             assert torch.allclose(u, v, atol=1e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize('E,Sh,r', [(2, 4, 1), (2, 4, 2), (2, 4, 4), (1, 2, 2), (3, 2, 1)])
+def test_virtual_geometry_of_sharded_experts_matches_repeat_view_sum(E, Sh, r):
+    """parallel/fused.py expresses experts sharded over Sh GPUs with r token copies as one virtual expert per GPU.  Emulated
+    with plain indexing, it must move exactly the rows the generic path moves with repeat / view / all-to-all / sum
+    (models/moe_layer.py; reference tutel/impls/moe_layer.py:331-357)."""
+    from tutel_b200.ops.dispatch import DispatchPlan, raw_decode, raw_encode
+    from tutel_b200.ops.routing import _locations
+    from tutel_b200.parallel.fused import _virtual_plan
+    torch.manual_seed(E * 100 + Sh * 10 + r)
+    S, k, M = 40, min(2, E), 6
+    W = E * Sh
+    scores = torch.rand(S, E)
+    idx = torch.topk(scores, k, dim=1).indices.t().contiguous().to(torch.int32)
+    loc, counts = _locations(idx, E)
+    C = 16                                    # some tokens are dropped; C * r divisible by Sh
+    plan = DispatchPlan(E, C, idx, loc.to(torch.int32))
+    x = torch.randn(S, M)
+    gates = torch.rand(k, S)
+    gpu_scale = torch.arange(1, W + 1, dtype=torch.float32).view(W, 1, 1)      # "expert compute" that differs per GPU
+
+    # generic path
+    enc = raw_encode(x, None, plan).view(E, C, M)
+    sent = enc.repeat(1, r, 1).view(W, -1, M)
+    back = (sent * gpu_scale).view(E, r, -1, M).sum(dim=1)
+    want = raw_decode(back.reshape(E * C, M), gates, plan)
+
+    # virtual geometry
+    vp = _virtual_plan(plan, E, Sh, r)
+    Cv = C * r // Sh
+    slot = vp.slot_src.view(W, Cv).long()
+    recv = torch.where((slot >= 0).unsqueeze(-1), x[(slot.clamp(min=0) // k)], torch.zeros(()))
+    out_buf = (recv * gpu_scale).reshape(W * Cv, M)
+    vplan = DispatchPlan(W, Cv, vp.idx_ks, vp.loc_ks)
+    got = raw_decode(out_buf, gates.repeat(r, 1), vplan)
+    assert torch.allclose(got, want, atol=1e-5)

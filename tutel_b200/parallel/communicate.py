@@ -224,7 +224,7 @@ def simple_reduce_scatter(input: torch.Tensor, group=None, op=dist.ReduceOp.SUM)
     if not input.is_cuda:
         return simple_split(simple_all_reduce(input, group, op=op), group=group)
     t = _p2p(group, input)
-    if t is not None and t.supports_reduce(input, op):
+    if t is not None and t.supports_reduce_scatter(input, op):
         return t.reduce_scatter(input, op)
     output = torch.empty_like(input[: input.size(0) // world_size])
     dist.reduce_scatter_tensor(output, input, op=op, group=group)

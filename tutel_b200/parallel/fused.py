@@ -259,6 +259,9 @@ class _Txn:
     def _push_tables(self, width: int):
         """Encode side: expert e's rows go to rank e // El, segment (e % El, my rank) of its IN buffer."""
         g, t, b = self.geo, self.eng.t, self.bufs
+        hit = b.tables.get(('pd', width)), b.tables.get(('ps',))
+        if hit[0] is not None and hit[1] is not None:
+            return hit[0].data_ptr(), hit[1].data_ptr()
         dst = [t.base_ptr(e // g.El) + b.off_in + ((e % g.El) * g.W + g.rank) * g.C * width * g.es for e in range(g.E)]
         sig = [t.base_ptr(e // g.El) + b.f_in + ((e % g.El) * g.W + g.rank) * _FLAGS_PER_SEG * 4 for e in range(g.E)]
         return self._table(('pd', width), dst), self._table(('ps',), sig)
@@ -266,6 +269,9 @@ class _Txn:
     def _combine_tables(self, width: int):
         """GEMM epilogue side: group (local expert, source rank) is written into the source rank's OUT buffer."""
         g, t, b = self.geo, self.eng.t, self.bufs
+        hit = b.tables.get(('cd', width)), b.tables.get(('cs',))
+        if hit[0] is not None and hit[1] is not None:
+            return hit[0].data_ptr(), hit[1].data_ptr()
         dst, sig = [], []
         for grp in range(g.G):
             el, src = divmod(grp, g.W)
@@ -299,9 +305,12 @@ class _Txn:
         NVLink bytes of the 16-bit push)."""
         g, eng, t, b = self.geo, self.eng, self.eng.t, self.bufs
         soff = self._scale_off(width)
-        dst = [t.base_ptr(e // g.El) + b.off_in + ((e % g.El) * g.W + g.rank) * g.C * width for e in range(g.E)]
-        scl = [t.base_ptr(e // g.El) + b.off_in + soff + ((e % g.El) * g.W + g.rank) * g.C * 4 for e in range(g.E)]
-        dst_tab, scl_tab = self._table(('pd8', width), dst), self._table(('psc8', width), scl)
+        if ('pd8', width) in b.tables:
+            dst_tab, scl_tab = b.tables[('pd8', width)].data_ptr(), b.tables[('psc8', width)].data_ptr()
+        else:
+            dst = [t.base_ptr(e // g.El) + b.off_in + ((e % g.El) * g.W + g.rank) * g.C * width for e in range(g.E)]
+            scl = [t.base_ptr(e // g.El) + b.off_in + soff + ((e % g.El) * g.W + g.rank) * g.C * 4 for e in range(g.E)]
+            dst_tab, scl_tab = self._table(('pd8', width), dst), self._table(('psc8', width), scl)
         _, sig_tab = self._push_tables(width)
         cur = torch.cuda.current_stream()
         eng.side.wait_stream(cur)
