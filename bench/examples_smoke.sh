@@ -14,7 +14,7 @@ run helloworld_switch $COMMON --dtype bfloat16 --num_local_experts -$N
 run helloworld_amp $COMMON
 run helloworld_ddp $COMMON --dtype bfloat16
 run helloworld_ddp_tutel $COMMON --dtype float32
-run helloworld_from_scratch $COMMON --dtype bfloat16
+run helloworld_from_scratch --num_steps 6 --model_dim 512 --hidden_size 1024 --num_samples 2048
 run helloworld_custom_gate_expert $COMMON --dtype bfloat16
 run helloworld_custom_expert_sharded $COMMON --dtype bfloat16
 run nccl_all_to_all_v

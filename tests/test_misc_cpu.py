@@ -200,3 +200,70 @@ def test_jit_launch_annotation_scanner():
         ext.jit_parse('void not_a_kernel(int* a) {}')
     with pytest.raises(RuntimeError):
         ext.jit_parse('// [thread_extent] blockIdx.x = 4')
+
+
+def test_fused_ring_spills_one_transaction_ahead():
+    """parallel/fused.py: transactions take buffer sets round robin; a set that still carries a lease (a forward whose
+    backward is pending) is spilled when it becomes the NEXT set - one transaction before it is re-used - and a geometry's
+    ring is keyed by the power-of-two row quantum, not by the exact capacity."""
+    import weakref
+    from tutel_b200.parallel import fused
+
+    class FakeTransport:
+        def __init__(self):
+            self.bump, self.ctrl = 0, 0
+
+        def can_alloc(self, n):
+            return True
+
+        def alloc(self, name, n):
+            self.bump += n
+            return self.bump - n
+
+        def ctrl_alloc(self, name, n):
+            self.ctrl += n
+            return self.ctrl - n
+
+    class FakeLease:
+        def __init__(self, bufs, log, tag):
+            self.bufs, self.log, self.tag = bufs, log, tag
+
+        def spill(self, stream):
+            self.log.append(self.tag)
+            self.bufs.holder = None
+
+    geo = fused._Geometry(W=2, rank=0, E=4, El=2, C=300, k=2, M=64, H=128, Mo=64, es=2)
+    assert geo.rows_quantum() == 512 and geo.key() == fused._Geometry(2, 0, 4, 2, 500, 2, 64, 128, 64, 2).key()
+    assert geo.key() != fused._Geometry(2, 0, 4, 2, 513, 2, 64, 128, 64, 2).key()
+    ring = fused._Ring(FakeTransport(), geo, 1)
+    assert len(ring.sets) == 3 and ring.usable()
+    log, leases = [], []
+
+    def forward(tag):
+        s = ring.next(None)
+        assert s.holder is None
+        lease = FakeLease(s, log, tag)
+        s.holder = weakref.ref(lease)
+        leases.append(lease)
+        return s
+
+    def backward(lease):
+        s = ring.next(None)
+        assert s.holder is None
+        if lease.bufs.holder is not None and lease.bufs.holder() is lease:
+            lease.bufs.holder = None
+        return s
+
+    # one layer: forward on set 0, backward on set 1, next forward on set 2, ... - nothing is ever spilled
+    for step in range(4):
+        forward('L0s%d' % step)
+        backward(leases[-1])
+    assert log == []
+    # four layers deep: the ring wraps while leases are alive -> each is spilled exactly once, before its set is handed out
+    log.clear(), leases.clear()
+    for layer in range(4):
+        forward('f%d' % layer)
+    assert log == ['f0', 'f1']               # set of f0 became "next" during f2, set of f1 during f3
+    for lease in reversed(leases):
+        backward(lease)
+    assert sorted(log) == ['f0', 'f1', 'f2', 'f3'][:len(log)] and len(log) == len(set(log))

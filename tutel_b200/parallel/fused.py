@@ -71,11 +71,19 @@ class _Geometry:
         self.G = El * W                                    # GEMM groups: (local expert, source rank)
         self.width = max(M, Mo)
 
+    def rows_quantum(self) -> int:
+        """Buffer sets are sized for the next power of two >= C (at least 256 rows): a capacity that changes from call to
+        call (dynamic / dropless capacity factors) re-uses a handful of rings instead of allocating one per distinct value."""
+        q = 256
+        while q < self.C:
+            q *= 2
+        return q
+
     def key(self):
-        return (self.W, self.E, self.El, self.C, self.width, self.es)
+        return (self.W, self.E, self.El, self.rows_quantum(), self.width, self.es)
 
     def set_bytes(self) -> int:
-        return 2 * self.E * self.C * self.width * self.es
+        return 2 * self.E * self.rows_quantum() * self.width * self.es
 
 
 class _Plan:
@@ -110,7 +118,7 @@ class _BufferSet:
     """One (IN, OUT) pair + flag areas at identical offsets on every rank."""
 
     def __init__(self, t: 'p2p.P2PTransport', tag: str, geo: _Geometry):
-        half = geo.E * geo.C * geo.width * geo.es
+        half = geo.E * geo.rows_quantum() * geo.width * geo.es
         self.off_in = t.alloc(tag + '/in', half)
         self.off_out = t.alloc(tag + '/out', half)
         self.f_in = t.ctrl_alloc(tag + '/f_in', geo.G * _FLAGS_PER_SEG * 4)
@@ -253,23 +261,28 @@ class _Txn:
         tab = self.bufs.tables.get(key)
         if tab is None:
             tab = torch.tensor(values, dtype=torch.int64, device='cuda')
-            self.bufs.tables[key] = tab
+            if len(self.bufs.tables) < 512:
+                self.bufs.tables[key] = tab
+            else:       # a capacity that keeps changing: stop caching, keep the last few alive for the kernels still queued
+                recent = self.bufs.tables.setdefault('__recent__', [])
+                recent.append(tab)
+                del recent[:-64]
         return tab.data_ptr()
 
     def _push_tables(self, width: int):
         """Encode side: expert e's rows go to rank e // El, segment (e % El, my rank) of its IN buffer."""
         g, t, b = self.geo, self.eng.t, self.bufs
-        hit = b.tables.get(('pd', width)), b.tables.get(('ps',))
+        hit = b.tables.get(('pd', width, g.C)), b.tables.get(('ps',))
         if hit[0] is not None and hit[1] is not None:
             return hit[0].data_ptr(), hit[1].data_ptr()
         dst = [t.base_ptr(e // g.El) + b.off_in + ((e % g.El) * g.W + g.rank) * g.C * width * g.es for e in range(g.E)]
         sig = [t.base_ptr(e // g.El) + b.f_in + ((e % g.El) * g.W + g.rank) * _FLAGS_PER_SEG * 4 for e in range(g.E)]
-        return self._table(('pd', width), dst), self._table(('ps',), sig)
+        return self._table(('pd', width, g.C), dst), self._table(('ps',), sig)
 
     def _combine_tables(self, width: int):
         """GEMM epilogue side: group (local expert, source rank) is written into the source rank's OUT buffer."""
         g, t, b = self.geo, self.eng.t, self.bufs
-        hit = b.tables.get(('cd', width)), b.tables.get(('cs',))
+        hit = b.tables.get(('cd', width, g.C)), b.tables.get(('cs',))
         if hit[0] is not None and hit[1] is not None:
             return hit[0].data_ptr(), hit[1].data_ptr()
         dst, sig = [], []
@@ -278,7 +291,7 @@ class _Txn:
             e = g.rank * g.El + el
             dst.append(t.base_ptr(src) + b.off_out + e * g.C * width * g.es)
             sig.append(t.base_ptr(src) + b.f_out + e * 4)
-        return self._table(('cd', width), dst), self._table(('cs',), sig)
+        return self._table(('cd', width, g.C), dst), self._table(('cs',), sig)
 
     # ---- the primitives ----
     def push(self, src: torch.Tensor, gates_f32: Optional[torch.Tensor], width: int) -> torch.cuda.Event:
@@ -305,12 +318,12 @@ class _Txn:
         NVLink bytes of the 16-bit push)."""
         g, eng, t, b = self.geo, self.eng, self.eng.t, self.bufs
         soff = self._scale_off(width)
-        if ('pd8', width) in b.tables:
-            dst_tab, scl_tab = b.tables[('pd8', width)].data_ptr(), b.tables[('psc8', width)].data_ptr()
+        if ('pd8', width, g.C) in b.tables:
+            dst_tab, scl_tab = b.tables[('pd8', width, g.C)].data_ptr(), b.tables[('psc8', width, g.C)].data_ptr()
         else:
             dst = [t.base_ptr(e // g.El) + b.off_in + ((e % g.El) * g.W + g.rank) * g.C * width for e in range(g.E)]
             scl = [t.base_ptr(e // g.El) + b.off_in + soff + ((e % g.El) * g.W + g.rank) * g.C * 4 for e in range(g.E)]
-            dst_tab, scl_tab = self._table(('pd8', width), dst), self._table(('psc8', width), scl)
+            dst_tab, scl_tab = self._table(('pd8', width, g.C), dst), self._table(('psc8', width, g.C), scl)
         _, sig_tab = self._push_tables(width)
         cur = torch.cuda.current_stream()
         eng.side.wait_stream(cur)
