@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "cpu_kernels.h"
+#include "gemm_mx.h"
 #include "gemm_sm100.h"
 #include "jit_nvrtc.h"
 #include "moe_kernels.h"
@@ -399,6 +400,47 @@ at::Tensor dequant_rows(const at::Tensor& q, const at::Tensor& scale, at::Scalar
   return y;
 }
 
+// MX block-scaled fp8 (OCP MX: e4m3 elements, one UE8M0 scale per 32 K elements); see csrc/gemm_mx.cu.
+// x [G, R, K] (16 bit, K % 128 == 0) -> [q e4m3 [G, R, K], sf uint8 (tile-ordered scale atoms, csrc/gemm_mx.h)]
+std::vector<at::Tensor> mx_quantize(const at::Tensor& x) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && x.dim() == 3 && x.element_size() == 2 && x.size(2) % 128 == 0,
+              "mx_quantize: contiguous 16-bit CUDA tensor [G, R, K] with K % 128 == 0 expected");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int G = static_cast<int>(x.size(0)), R = static_cast<int>(x.size(1)), K = static_cast<int>(x.size(2));
+  at::Tensor q = at::empty({G, R, K}, x.options().dtype(at::kFloat8_e4m3fn));
+  const long long sf_bytes = tb::mx_sf_bytes(G, R, K);
+  at::Tensor sf = (R % 128 == 0) ? at::empty({sf_bytes}, x.options().dtype(at::kByte))
+                                 : at::zeros({sf_bytes}, x.options().dtype(at::kByte));
+  TB_CHECK_CUDA(tb::mx_quantize(x.data_ptr(), q.data_ptr(), sf.data_ptr(), G, R, K, elem_type_of(x), cur_stream()));
+  return {q, sf};
+}
+
+// d[g] = a[g] * b[g]^T :  a e4m3 [G, M, K], b e4m3 [G, N, K], scales from mx_quantize -> bf16 [G, M, N]
+at::Tensor mx_gemm(const at::Tensor& a, const at::Tensor& sfa, const at::Tensor& b, const at::Tensor& sfb, bool relu,
+                   int64_t block_n, bool sf_addr_plain) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && sfa.is_cuda() && sfb.is_cuda() && a.dim() == 3 && b.dim() == 3);
+  TORCH_CHECK(a.is_contiguous() && b.is_contiguous() && sfa.is_contiguous() && sfb.is_contiguous());
+  TORCH_CHECK(a.scalar_type() == at::kFloat8_e4m3fn && b.scalar_type() == at::kFloat8_e4m3fn &&
+              sfa.scalar_type() == at::kByte && sfb.scalar_type() == at::kByte, "mx_gemm: e4m3 operands and uint8 scales expected");
+  TORCH_CHECK(a.size(0) == b.size(0) && a.size(2) == b.size(2), "mx_gemm: a [G, M, K] and b [G, N, K] expected");
+  const c10::cuda::CUDAGuard guard(a.device());
+  tb::MxGemmProblem p;
+  p.G = static_cast<int>(a.size(0)); p.M = static_cast<int>(a.size(1)); p.K = static_cast<int>(a.size(2));
+  p.N = static_cast<int>(b.size(1));
+  TORCH_CHECK(sfa.numel() == tb::mx_sf_bytes(p.G, p.M, p.K) && sfb.numel() == tb::mx_sf_bytes(p.G, p.N, p.K),
+              "mx_gemm: scale arrays do not match the operand shapes");
+  at::Tensor d = at::empty({p.G, p.M, p.N}, a.options().dtype(at::kBFloat16));
+  p.a = a.data_ptr(); p.sfa = sfa.data_ptr(); p.b = b.data_ptr(); p.sfb = sfb.data_ptr(); p.d = d.data_ptr();
+  p.ldd = p.N; p.d_group_stride = static_cast<long long>(p.M) * p.N;
+  p.relu = relu ? 1 : 0;
+  p.block_n = static_cast<int>(block_n);
+  p.sf_addr_plain = sf_addr_plain ? 1 : 0;
+  const char* why = nullptr;
+  cudaError_t e = tb::mx_gemm_launch(p, cur_stream(), &why);
+  TORCH_CHECK(e == cudaSuccess, "mx_gemm: ", why ? why : cudaGetErrorString(e));
+  return d;
+}
+
 // Gated-linear-unit GEMMs (SwiGLU / GeGLU / ReGLU experts; reference: tutel/experts/llama_ffn.py:38-41 runs three
 // cuBLAS GEMMs plus separate activation and multiply kernels).
 //   forward  (b2 given):  h = act(a*b) .* (a*b2)   [+ g = a*b -> d2, u = a*b2 -> d3 when given]   ONE launch
@@ -554,6 +596,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("quantize_rows", &quantize_rows);
   m.def("dequant_rows", &dequant_rows);
   m.def("quantize_transpose", &quantize_transpose);
+  m.def("mx_quantize", &mx_quantize);
+  m.def("mx_gemm", &mx_gemm);
   register_symm_bindings(m);
   register_cpu_bindings(m);
   register_jit_bindings(m);
