@@ -37,7 +37,8 @@ def parse():
     ap.add_argument('--overlap', type=int, default=1)
     ap.add_argument('--no_e2e', action='store_true')
     ap.add_argument('--expert_type', type=str, default='ffn')     # llama_ffn: Mixtral-style SwiGLU block (BASELINE config #3)
-    ap.add_argument('--fp8', action='store_true')                  # ours only: e4m3 forward GEMMs
+    ap.add_argument('--fp8', action='store_true')                  # ours only: e4m3 forward + data-gradient GEMMs
+    ap.add_argument('--fp8_mode', default='row', choices=['row', 'mx'])   # row scales (fused engine) or MX 32-element block scales
     return ap.parse_args()
 
 
@@ -80,7 +81,7 @@ def main():
                 experts=dict({'type': args.expert_type, 'num_experts_per_device': local_experts,
                               'hidden_size_per_expert': args.hidden},
                              **({'activation_fn': (lambda x: F.relu(x))} if args.expert_type == 'ffn' else {}),
-                             **({'fp8': True} if (args.fp8 and args.impl == 'ours') else {})),
+                             **({'fp8': args.fp8_mode} if (args.fp8 and args.impl == 'ours') else {})),
                 model_dim=args.model_dim,
                 scan_expert_func=lambda name, param: setattr(param, 'skip_allreduce', True),
                 seeds=(1, rank + 1, 1),
@@ -241,10 +242,10 @@ def main():
     out = {
         'metric': 'moe_layer_fwd_bwd_tokens_per_sec', 'value': value, 'unit': 'tokens/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': warm_done, 'warmup_requested': args.warmup, 'warmup_ms_per_step_trace': warm_trace, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if not (args.fp8 and args.impl == 'ours') else 'bf16 (fp8 e4m3 expert GEMMs)', 'data': 'synthetic (random tokens, random-init weights)',
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if not (args.fp8 and args.impl == 'ours') else 'bf16 (fp8 e4m3 expert GEMMs, %s scales)' % args.fp8_mode, 'data': 'synthetic (random tokens, random-init weights)',
         'impl': args.impl,
         'config': {'model': 'helloworld moe_layer top-%d %d-expert %s%s model_dim=%d hidden=%d' % (
-            args.top, args.experts, 'ffn(relu)' if args.expert_type == 'ffn' else args.expert_type, ' fp8-forward' if args.fp8 else '', args.model_dim, args.hidden),
+            args.top, args.experts, 'ffn(relu)' if args.expert_type == 'ffn' else args.expert_type, (' fp8-' + args.fp8_mode) if args.fp8 else '', args.model_dim, args.hidden),
                    'global_batch': world * BATCH, 'seq_len': TOKENS, 'tokens_per_gpu': BATCH * TOKENS,
                    'parallelism': 'ep%d (%d local experts/GPU)' % (world, local_experts), 'capacity_factor': 1.0,
                    'step': 'zero_grad + fwd + nll_loss + bwd (incl. input gradient) + gate-grad all-reduce + SGD',

@@ -1,4 +1,4 @@
-"""B200 check of the MX block-scaled GEMM (csrc/gemm_mx.cu): exactness on crafted operands, agreement with the PyTorch
+"""B200 check of the MX block-scaled GEMM (csrc/gemm_mx.cu): exactness on crafted operands (full grid and 5 persistent CTAs), agreement with the PyTorch
 definition on random data, throughput next to the row-scaled fp8 and bf16 GEMMs.
 
     python bench/mx_check.py [--out gpurun_out/mx] [--no_perf]
@@ -34,7 +34,7 @@ def crafted(mode, G, M, N, K, dev, seed=0):
     return a.to(dev), ea.to(dev), b.to(dev), eb.to(dev)
 
 
-def run_exact(tag, mode, G, M, N, K, block_n, plain):
+def run_exact(tag, mode, G, M, N, K, block_n, small_grid):
     import torch
     from tutel_b200.ops import mx
     dev = torch.device('cuda')
@@ -42,11 +42,11 @@ def run_exact(tag, mode, G, M, N, K, block_n, plain):
     aq, bq = a.to(torch.float8_e4m3fn), b.to(torch.float8_e4m3fn)
     sa, sb = mx.pack_scales(ea), mx.pack_scales(eb)
     ref = torch.matmul(mx.mx_dequantize(aq, sa), mx.mx_dequantize(bq, sb).transpose(1, 2))
-    y = mx.mx_gemm(aq, sa, bq, sb, block_n=block_n, _sf_addr_plain=plain)
+    y = mx.mx_gemm(aq, sa, bq, sb, block_n=block_n, max_ctas=(5 if small_grid else 0))
     torch.cuda.synchronize()
     want = ref.to(torch.bfloat16).float()
     bad = (y.float() != want)
-    rec = {'case': tag, 'mode': mode, 'shape': [G, M, N, K], 'block_n': block_n, 'plain': plain,
+    rec = {'case': tag, 'mode': mode, 'shape': [G, M, N, K], 'block_n': block_n, 'max_ctas': 5 if small_grid else 0,
            'mismatch': int(bad.sum()), 'of': bad.numel(), 'max_abs': float((y.float() - want).abs().max())}
     if rec['mismatch']:
         idx = bad.nonzero()[:6].tolist()
@@ -61,7 +61,7 @@ def run_exact(tag, mode, G, M, N, K, block_n, plain):
     return rec['mismatch'] == 0
 
 
-def group_exact(plain, quick):
+def group_exact(small_grid, quick):
     import torch
     from tutel_b200.ops import backend
     backend.require_ext().set_spin_timeout(5.0)
@@ -72,8 +72,8 @@ def group_exact(plain, quick):
         cases += [('wrap', 'random', 2, 200, 384, 512, 128), ('bn256', 'random', 1, 256, 512, 1024, 256),
                   ('bn256rows', 'rows', 1, 128, 256, 128, 256), ('big', 'random', 2, 1000, 1024, 2048, 0)]
     for tag, mode, G, M, N, K, bn in cases:
-        ok = run_exact(tag, mode, G, M, N, K, bn, plain) and ok
-    print(json.dumps({'group': 'exact', 'plain': plain, 'ok': ok}), flush=True)
+        ok = run_exact(tag, mode, G, M, N, K, bn, small_grid) and ok
+    print(json.dumps({'group': 'exact', 'max_ctas': 5 if small_grid else 0, 'ok': ok}), flush=True)
 
 
 def group_random():
@@ -97,7 +97,7 @@ def group_random():
         full = torch.matmul(x.float(), w.float().transpose(1, 2))
         err_def = float((y - ref).abs().max() / ref.abs().max())
         err_full = float((y - full).norm() / full.norm())
-        yr = mx.mx_gemm(xq, xs, wq, ws, relu=True).float()
+        yr = mx.mx_gemm(xq, xs, wq, ws, epilogue=mx.EPI_RELU).float()
         relu_ok = bool((yr == torch.relu(y)).all())
         good = same_q and same_s and err_def < 8e-3 and err_full < 0.06 and relu_ok
         ok = ok and good
@@ -153,8 +153,49 @@ def group_perf():
         rec['mx_quantize_gbps'] = round((x.numel() * 3 + xs.numel()) / ms / 1e6, 1)
         ms = timeit(lambda: gemm.quantize_rows(x))
         rec['row_quantize_ms'] = round(ms, 4)
+        ms = timeit(lambda: mx.mx_quantize_transpose(w))
+        rec['mx_quantize_transpose_ms'] = round(ms, 4)
+        rec['mx_quantize_transpose_gbps'] = round(w.numel() * 3 / ms / 1e6, 1)
+        bias = torch.randn(G, N, device='cuda', dtype=torch.bfloat16)
+        ms = timeit(lambda: mx.mx_gemm(xq, xs, wq, ws, bias=bias, epilogue=mx.EPI_RELU))
+        rec['mx_bias_relu_ms'] = round(ms, 4)
         print(json.dumps(rec), flush=True)
         out.append(rec)
+    # expert FFN of the flagship layer on one GPU (8 experts x 1024 rows, 4096 -> 14336 -> 4096), forward + backward
+    E, C, M, H = 8, 1024, 4096, 14336
+    x = torch.randn(E, C, M, device='cuda', dtype=torch.bfloat16, requires_grad=True)
+    w1 = (torch.randn(E, H, M, device='cuda') * M ** -0.5).to(torch.bfloat16).requires_grad_()
+    w2 = (torch.randn(E, H, M, device='cuda') * H ** -0.5).to(torch.bfloat16).requires_grad_()
+    b1 = torch.zeros(E, H, device='cuda', dtype=torch.bfloat16, requires_grad=True)
+    b2 = torch.zeros(E, M, device='cuda', dtype=torch.bfloat16, requires_grad=True)
+    dy = torch.randn(E, C, M, device='cuda', dtype=torch.bfloat16)
+    rec = {'ffn_shape': [E, C, M, H]}
+    modes = {'bf16': lambda: gemm.fused_act_ffn(x, w1, b1, w2, b2, None, 'relu'),
+             'fp8_row': lambda: gemm.fused_relu_ffn_fp8(x, w1, b1, w2, b2),
+             'fp8_mx': lambda: mx.fused_relu_ffn_mx(x, w1, b1, w2, b2)}
+    ref = None
+    for name, fn in modes.items():
+        def step():
+            for t in (x, w1, w2, b1, b2):
+                t.grad = None
+            y = fn()
+            y.backward(dy)
+            return y
+        ms = timeit(step, iters=10)               # weights unchanged between iterations: quantised copies are cached
+        y = step()
+        if ref is None:
+            ref = (y.detach().float(), x.grad.float().clone())
+        rec[name + '_fwd_bwd_ms'] = round(ms, 3)
+        rec[name + '_y_rel_err'] = round(float((y.detach().float() - ref[0]).norm() / ref[0].norm()), 4)
+        rec[name + '_dx_rel_err'] = round(float((x.grad.float() - ref[1]).norm() / ref[1].norm()), 4)
+
+        def requant():
+            gemm.invalidate_fp8_cache()
+            return fn()
+        if name != 'bf16':
+            rec[name + '_fwd_with_weight_quantisation_ms'] = round(timeit(requant, iters=5), 3)
+            rec[name + '_fwd_ms'] = round(timeit(fn, iters=10), 3)
+    print(json.dumps(rec), flush=True)
     print(json.dumps({'group': 'perf', 'ok': True}), flush=True)
 
 
@@ -162,19 +203,19 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default='gpurun_out/mx')
     ap.add_argument('--group', default=None)
-    ap.add_argument('--plain', type=int, default=0)
+    ap.add_argument('--small_grid', type=int, default=0)     # 5 persistent CTAs: every CTA walks several tiles
     ap.add_argument('--quick', type=int, default=0)
     ap.add_argument('--no_perf', action='store_true')
     args = ap.parse_args()
     if args.group == 'exact':
-        return group_exact(bool(args.plain), bool(args.quick))
+        return group_exact(bool(args.small_grid), bool(args.quick))
     if args.group == 'random':
         return group_random()
     if args.group == 'perf':
         return group_perf()
     os.makedirs(args.out, exist_ok=True)
-    plan = [('exact_sub', ['--group', 'exact', '--plain', '0'], 240),
-            ('exact_plain_quick', ['--group', 'exact', '--plain', '1', '--quick', '1'], 100),
+    plan = [('exact_sub', ['--group', 'exact'], 240),
+            ('exact_small_grid', ['--group', 'exact', '--small_grid', '1'], 100),
             ('random', ['--group', 'random'], 150)]
     if not args.no_perf:
         plan.append(('perf', ['--group', 'perf'], 200))

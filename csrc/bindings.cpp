@@ -415,9 +415,25 @@ std::vector<at::Tensor> mx_quantize(const at::Tensor& x) {
   return {q, sf};
 }
 
-// d[g] = a[g] * b[g]^T :  a e4m3 [G, M, K], b e4m3 [G, N, K], scales from mx_quantize -> bf16 [G, M, N]
-at::Tensor mx_gemm(const at::Tensor& a, const at::Tensor& sfa, const at::Tensor& b, const at::Tensor& sfb, bool relu,
-                   int64_t block_n, bool sf_addr_plain) {
+// x [G, R, K] (16 bit, R % 128 == 0, K % 64 == 0) -> [qT e4m3 [G, K, R] quantised along R, sf]
+std::vector<at::Tensor> mx_quantize_transpose(const at::Tensor& x) {
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && x.dim() == 3 && x.element_size() == 2 && x.size(1) % 128 == 0 && x.size(2) % 64 == 0,
+              "mx_quantize_transpose: contiguous 16-bit CUDA tensor [G, R, K] with R % 128 == 0 and K % 64 == 0 expected");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int G = static_cast<int>(x.size(0)), R = static_cast<int>(x.size(1)), K = static_cast<int>(x.size(2));
+  at::Tensor q = at::empty({G, K, R}, x.options().dtype(at::kFloat8_e4m3fn));
+  const long long sf_bytes = tb::mx_sf_bytes(G, K, R);
+  at::Tensor sf = (K % 128 == 0) ? at::empty({sf_bytes}, x.options().dtype(at::kByte))
+                                 : at::zeros({sf_bytes}, x.options().dtype(at::kByte));
+  TB_CHECK_CUDA(tb::mx_quantize_transpose(x.data_ptr(), q.data_ptr(), sf.data_ptr(), G, R, K, elem_type_of(x), cur_stream()));
+  return {q, sf};
+}
+
+// d[g] = epilogue(a[g] * b[g]^T + bias[g]) :  a e4m3 [G, M, K], b e4m3 [G, N, K], scales from mx_quantize -> bf16 [G, M, N]
+// epilogue: 0 none, 1 ReLU, 2 ReLU backward (d = aux > 0 ? acc : 0 with aux bf16 [G, M, N])
+at::Tensor mx_gemm(const at::Tensor& a, const at::Tensor& sfa, const at::Tensor& b, const at::Tensor& sfb,
+                   const c10::optional<at::Tensor>& bias, const c10::optional<at::Tensor>& aux, int64_t epilogue,
+                   int64_t block_n, int64_t max_ctas) {
   TORCH_CHECK(a.is_cuda() && b.is_cuda() && sfa.is_cuda() && sfb.is_cuda() && a.dim() == 3 && b.dim() == 3);
   TORCH_CHECK(a.is_contiguous() && b.is_contiguous() && sfa.is_contiguous() && sfb.is_contiguous());
   TORCH_CHECK(a.scalar_type() == at::kFloat8_e4m3fn && b.scalar_type() == at::kFloat8_e4m3fn &&
@@ -432,9 +448,19 @@ at::Tensor mx_gemm(const at::Tensor& a, const at::Tensor& sfa, const at::Tensor&
   at::Tensor d = at::empty({p.G, p.M, p.N}, a.options().dtype(at::kBFloat16));
   p.a = a.data_ptr(); p.sfa = sfa.data_ptr(); p.b = b.data_ptr(); p.sfb = sfb.data_ptr(); p.d = d.data_ptr();
   p.ldd = p.N; p.d_group_stride = static_cast<long long>(p.M) * p.N;
-  p.relu = relu ? 1 : 0;
+  if (bias.has_value() && bias->defined()) {
+    TORCH_CHECK(bias->is_cuda() && bias->scalar_type() == at::kBFloat16 && bias->is_contiguous() && bias->numel() == static_cast<long long>(p.G) * p.N,
+                "mx_gemm: bias must be a contiguous bf16 [G, N]");
+    p.bias = bias->data_ptr(); p.bias_group_stride = p.N;
+  }
+  if (aux.has_value() && aux->defined()) {
+    TORCH_CHECK(aux->is_cuda() && aux->scalar_type() == at::kBFloat16 && aux->is_contiguous() && aux->numel() == d.numel(),
+                "mx_gemm: aux must be a contiguous bf16 [G, M, N]");
+    p.aux = aux->data_ptr(); p.ld_aux = p.N; p.aux_group_stride = p.d_group_stride;
+  }
+  p.epilogue = static_cast<int>(epilogue);
   p.block_n = static_cast<int>(block_n);
-  p.sf_addr_plain = sf_addr_plain ? 1 : 0;
+  p.max_ctas = static_cast<int>(max_ctas);
   const char* why = nullptr;
   cudaError_t e = tb::mx_gemm_launch(p, cur_stream(), &why);
   TORCH_CHECK(e == cudaSuccess, "mx_gemm: ", why ? why : cudaGetErrorString(e));
@@ -597,6 +623,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dequant_rows", &dequant_rows);
   m.def("quantize_transpose", &quantize_transpose);
   m.def("mx_quantize", &mx_quantize);
+  m.def("mx_quantize_transpose", &mx_quantize_transpose);
   m.def("mx_gemm", &mx_gemm);
   register_symm_bindings(m);
   register_cpu_bindings(m);

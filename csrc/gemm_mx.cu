@@ -12,9 +12,11 @@
 //               the four lane quarters) followed by four K=32 MMAs whose descriptors select byte 0..3 of those columns;
 //               tcgen05.commit releases the stage.  tcgen05.cp and tcgen05.mma of one thread execute in issue order,
 //               so the scale columns are single-buffered.
-//   warps 2-5   epilogue: tcgen05.ld (thread = accumulator row), optional ReLU, bf16, 16-byte global stores
-// BN = 256: 4 stages (198 KB), one CTA per SM.  BN = 128: 3 stages (100 KB) so that TWO CTAs share an SM (TMEM 2 x 256
-// columns) and one's epilogue hides behind the other's main loop.
+//   warps 2-5   epilogue: tcgen05.ld (thread = accumulator row) -> bias / ReLU in fp32 -> packed bf16 in registers ->
+//               accumulator released -> (ReLU-backward mask) -> 16-byte global stores, overlapping the next tile
+// Persistent (one CTA per SM for BN = 256: 4 stages, 198 KB; two per SM for BN = 128: 3 stages, 100 KB, TMEM 2 x 256
+// columns).  Tensor memory holds ONE accumulator (BN columns) plus 4 + BN / 32 scale columns: a second 256-column
+// accumulator would not leave room for the scales, hence the register hand-off instead of double buffering.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -59,8 +61,12 @@ struct MxArgs {
   int M, N, K, G;
   int tiles_m, tiles_n;
   int sfa_row_tiles, sfb_row_tiles;   // 128-row tiles of the scale arrays
-  int relu;
-  int sf_addr_plain;   // debug: do not mirror the scale byte index into bits [30,32) of the scale TMEM addresses
+  const __nv_bfloat16* bias;          // [G, N] or null
+  long long bias_group_stride;
+  const __nv_bfloat16* aux;           // MX_EPI_RELU_BWD: forward activation [G, M, N]
+  long long ld_aux, aux_group_stride;
+  long long num_tiles;
+  int epi;
 };
 
 __device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
@@ -115,7 +121,8 @@ mx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
   const uint32_t tfull_bar = bar_base + 128u;
-  const uint32_t tmem_slot = bar_base + 136u;
+  const uint32_t tempty_bar = bar_base + 136u;
+  const uint32_t tmem_slot = bar_base + 144u;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
   if (warp == 0 && ptx::elect_one()) {
@@ -128,6 +135,7 @@ mx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_init(empty_bar(s), 1);
     }
     ptx::mbar_init(tfull_bar, 1);
+    ptx::mbar_init(tempty_bar, 4);     // one arrival per epilogue warp
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc<1>(tmem_slot, C::TMEM_COLS);
@@ -135,100 +143,148 @@ mx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
-
-  int g, m_blk, n_blk;
-  decode_tile(blockIdx.x, args.tiles_m, args.tiles_n, g, m_blk, n_blk);
-  const int m0 = m_blk * kBM;
-  const int n0 = n_blk * BN;
   const int num_kb = args.K / kBK;
 
+  // Persistent: CTA b works on tiles b, b + gridDim.x, ...; the TMA producer runs ahead into the next tile while the
+  // epilogue warps still hold the previous one in registers.
   if (warp == 0) {
     // =============================== TMA producer ===============================
     int s = 0;
     uint32_t ph = 0;
-    const uint8_t* sfa_g = args.sfa + static_cast<long long>(g) * num_kb * args.sfa_row_tiles * kSfAtomBytes;
-    const uint8_t* sfb_g = args.sfb + static_cast<long long>(g) * num_kb * args.sfb_row_tiles * kSfAtomBytes;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-      if (ptx::elect_one()) {
-        const uint32_t fb = full_bar(s);
-        ptx::mbar_expect_tx(fb, C::OP_BYTES + C::SF_BYTES);
-        ptx::tma_load_3d(smem_a(s), &tmA, fb, kb * kBK, m0, g);
-        ptx::tma_load_3d(smem_b(s), &tmB, fb, kb * kBK, n0, g);
-        bulk_load(smem_sfa(s), sfa_g + (static_cast<long long>(kb) * args.sfa_row_tiles + m_blk) * kSfAtomBytes,
-                  kSfAtomBytes, fb);
-        bulk_load(smem_sfb(s),
-                  sfb_g + (static_cast<long long>(kb) * args.sfb_row_tiles + n_blk * (BN / 128)) * kSfAtomBytes,
-                  C::SFB_BYTES, fb);
+    for (long long t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+      int g, m_blk, n_blk;
+      decode_tile(t, args.tiles_m, args.tiles_n, g, m_blk, n_blk);
+      const int m0 = m_blk * kBM, n0 = n_blk * BN;
+      const uint8_t* sfa_g = args.sfa + static_cast<long long>(g) * num_kb * args.sfa_row_tiles * kSfAtomBytes;
+      const uint8_t* sfb_g = args.sfb + static_cast<long long>(g) * num_kb * args.sfb_row_tiles * kSfAtomBytes;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+        if (ptx::elect_one()) {
+          const uint32_t fb = full_bar(s);
+          ptx::mbar_expect_tx(fb, C::OP_BYTES + C::SF_BYTES);
+          ptx::tma_load_3d(smem_a(s), &tmA, fb, kb * kBK, m0, g);
+          ptx::tma_load_3d(smem_b(s), &tmB, fb, kb * kBK, n0, g);
+          bulk_load(smem_sfa(s), sfa_g + (static_cast<long long>(kb) * args.sfa_row_tiles + m_blk) * kSfAtomBytes,
+                    kSfAtomBytes, fb);
+          bulk_load(smem_sfb(s),
+                    sfb_g + (static_cast<long long>(kb) * args.sfb_row_tiles + n_blk * (BN / 128)) * kSfAtomBytes,
+                    C::SFB_BYTES, fb);
+        }
+        __syncwarp();
+        if (++s == C::STAGES) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
-      if (++s == C::STAGES) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     int s = 0;
-    uint32_t ph = 0;
+    uint32_t ph = 0, tph = 0;
     // Operand descriptors: K-major, SWIZZLE_128B, 8-row groups 1024 B apart; a K=32 step advances the start by 32 B.
     constexpr uint32_t op_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     // Scale descriptors: K-major, no swizzle: 8-row x 16-byte core matrices of 128 contiguous bytes, 128 B apart.
     constexpr uint32_t sf_hi = (128u >> 4) | (1u << 14);
     // Instruction descriptor (block-scaled form): A/B format e4m3 (0), both K-major, N >> 3 at [17,23),
     // scale format UE8M0 at [23], M >> 4 at [24,29); the scale byte of a K=32 step goes to [4,6) (B) and [29,31) (A).
+    // (The same byte index is mirrored into bits [30,32) of the scale addresses, as CUTLASS does; measured: the
+    // hardware takes it from the descriptor, results are identical without the mirror.)
     constexpr uint32_t idesc0 = (static_cast<uint32_t>(BN >> 3) << 17) | (1u << 23) | (static_cast<uint32_t>(kBM >> 4) << 24);
     const uint32_t d_tmem = tmem_base;
     const uint32_t sfa_tmem = tmem_base + C::SFA_COL;
     const uint32_t sfb_tmem = tmem_base + C::SFB_COL;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      ptx::mbar_wait(full_bar(s), ph);
+    for (long long t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+      ptx::mbar_wait(tempty_bar, tph ^ 1u);     // the epilogue warps have read the previous tile out of TMEM
       ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint32_t a_lo = ((smem_a(s) >> 4) & 0x3FFFu) | (1u << 16);
-        const uint32_t b_lo = ((smem_b(s) >> 4) & 0x3FFFu) | (1u << 16);
-        tmem_cp_32x128b_warpx4(sfa_tmem, (static_cast<uint64_t>(sf_hi) << 32) | ((smem_sfa(s) >> 4) & 0x3FFFu) | (1u << 16));
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(full_bar(s), ph);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t a_lo = ((smem_a(s) >> 4) & 0x3FFFu) | (1u << 16);
+          const uint32_t b_lo = ((smem_b(s) >> 4) & 0x3FFFu) | (1u << 16);
+          tmem_cp_32x128b_warpx4(sfa_tmem, (static_cast<uint64_t>(sf_hi) << 32) | ((smem_sfa(s) >> 4) & 0x3FFFu) | (1u << 16));
 #pragma unroll
-        for (int j = 0; j < BN / 128; ++j)
-          tmem_cp_32x128b_warpx4(sfb_tmem + 4u * j, (static_cast<uint64_t>(sf_hi) << 32) |
-                                                        (((smem_sfb(s) + j * kSfAtomBytes) >> 4) & 0x3FFFu) | (1u << 16));
+          for (int j = 0; j < BN / 128; ++j)
+            tmem_cp_32x128b_warpx4(sfb_tmem + 4u * j, (static_cast<uint64_t>(sf_hi) << 32) |
+                                                          (((smem_sfb(s) + j * kSfAtomBytes) >> 4) & 0x3FFFu) | (1u << 16));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = (static_cast<uint64_t>(op_hi) << 32) | (a_lo + 2u * k);
-          const uint64_t bd = (static_cast<uint64_t>(op_hi) << 32) | (b_lo + 2u * k);
-          const uint32_t idesc = idesc0 | (static_cast<uint32_t>(k) << 4) | (static_cast<uint32_t>(k) << 29);
-          const uint32_t sub = args.sf_addr_plain ? 0u : (static_cast<uint32_t>(k) << 30);
-          umma_mxf8(d_tmem, ad, bd, idesc, sfa_tmem + sub, sfb_tmem + sub, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = (static_cast<uint64_t>(op_hi) << 32) | (a_lo + 2u * k);
+            const uint64_t bd = (static_cast<uint64_t>(op_hi) << 32) | (b_lo + 2u * k);
+            const uint32_t idesc = idesc0 | (static_cast<uint32_t>(k) << 4) | (static_cast<uint32_t>(k) << 29);
+            const uint32_t sub = static_cast<uint32_t>(k) << 30;
+            umma_mxf8(d_tmem, ad, bd, idesc, sfa_tmem + sub, sfb_tmem + sub, (kb | k) != 0);
+          }
+          ptx::umma_commit<1>(empty_bar(s));
+          if (kb == num_kb - 1) ptx::umma_commit<1>(tfull_bar);
         }
-        ptx::umma_commit<1>(empty_bar(s));
-        if (kb == num_kb - 1) ptx::umma_commit<1>(tfull_bar);
+        __syncwarp();
+        if (++s == C::STAGES) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
-      if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+      tph ^= 1u;
     }
   } else {
     // =============================== epilogue ===============================
+    // Phase A moves the whole accumulator row of this thread into registers as packed bf16 (bias / ReLU applied in
+    // fp32 on the way) and hands TMEM back to the MMA warp; phase B (ReLU-backward mask, global stores) then overlaps
+    // the next tile's main loop.  There is only ONE accumulator buffer: 2 x 256 columns would leave no room for the
+    // scale columns in the 512-column tensor memory.
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int row = m0 + q * 32 + lane;
-    ptx::mbar_wait(tfull_bar, 0);
-    ptx::tc_fence_after();
-    __nv_bfloat16* drow = args.d + static_cast<long long>(g) * args.d_group_stride + static_cast<long long>(row) * args.ldd + n0;
-    const bool relu = args.relu != 0;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), r);
-      ptx::tmem_ld_wait();
+    uint32_t tph = 0;
+    const int epi = args.epi;
+    for (long long t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+      int g, m_blk, n_blk;
+      decode_tile(t, args.tiles_m, args.tiles_n, g, m_blk, n_blk);
+      const int n0 = n_blk * BN;
+      const int row = m_blk * kBM + q * 32 + lane;
+      const __nv_bfloat16* bias = args.bias == nullptr ? nullptr : args.bias + static_cast<long long>(g) * args.bias_group_stride + n0;
+      uint32_t pk[BN / 2];
+      ptx::mbar_wait(tfull_bar, tph);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), r);
+        uint4 braw[4];                    // 32 bias values (bf16), fetched while the TMEM load is in flight
+        if (bias != nullptr) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) braw[v] = __ldg(reinterpret_cast<const uint4*>(bias + c * 32 + v * 8));
+        } else {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) braw[v] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        ptx::tmem_ld_wait();
+        const uint32_t* bw = reinterpret_cast<const uint32_t*>(braw);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          // a bf16 is the upper half of the fp32 with the same value
+          float lo = __uint_as_float(r[2 * j]) + __uint_as_float(bw[j] << 16);
+          float hi = __uint_as_float(r[2 * j + 1]) + __uint_as_float(bw[j] & 0xFFFF0000u);
+          if (epi == MX_EPI_RELU) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+          const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+          pk[c * 16 + j] = *reinterpret_cast<const uint32_t*>(&p);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar);
+      tph ^= 1u;
       if (row < args.M) {
+        __nv_bfloat16* drow = args.d + static_cast<long long>(g) * args.d_group_stride + static_cast<long long>(row) * args.ldd + n0;
+        const __nv_bfloat16* arow = (epi == MX_EPI_RELU_BWD)
+            ? args.aux + static_cast<long long>(g) * args.aux_group_stride + static_cast<long long>(row) * args.ld_aux + n0 : nullptr;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          uint32_t w[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float lo = __uint_as_float(r[v * 8 + 2 * j]);
-            float hi = __uint_as_float(r[v * 8 + 2 * j + 1]);
-            if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
-            const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
-            w[j] = *reinterpret_cast<const uint32_t*>(&p);
+        for (int v = 0; v < BN / 8; ++v) {
+          uint4 w = make_uint4(pk[v * 4], pk[v * 4 + 1], pk[v * 4 + 2], pk[v * 4 + 3]);
+          if (epi == MX_EPI_RELU_BWD) {
+            // keep the gradient where the forward activation (bf16 pairs in `a`) was positive
+            const uint4 a = ptx::ld_nc_v4(arow + v * 8);
+            auto keep = [](uint32_t x) {
+              uint32_t m = 0u;
+              if ((x & 0x8000u) == 0u && (x & 0x7FFFu) != 0u) m |= 0xFFFFu;
+              if ((x & 0x80000000u) == 0u && (x & 0x7FFF0000u) != 0u) m |= 0xFFFF0000u;
+              return m;
+            };
+            w.x &= keep(a.x); w.y &= keep(a.y); w.z &= keep(a.z); w.w &= keep(a.w);
           }
-          *reinterpret_cast<uint4*>(drow + c * 32 + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(drow + v * 8) = w;
         }
       }
     }
@@ -296,6 +352,53 @@ mx_quantize_kernel(const T* __restrict__ x, uint8_t* __restrict__ q, uint8_t* __
   }
 }
 
+// Transposing variant for weights: x [G, R, K] -> qT [G, K, R] quantised along R (the operand of a GEMM that reduces over
+// R), without materialising the 16-bit transpose.  One block = 128 (R) x 64 (K) tile through shared memory; thread
+// (k, rb) owns the 32 values x[r0 + 32 rb .. +32, k0 + k]: one scale, 32 output bytes (one full sector).
+constexpr int kTrR = 128, kTrK = 64, kTrPitch = kTrK + 2;   // pitch in elements: 33 words -> conflict-free both ways
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+mx_quantize_transpose_kernel(const T* __restrict__ x, uint8_t* __restrict__ qT, uint8_t* __restrict__ sf, int R, int K,
+                             int row_tiles) {
+  __shared__ __align__(16) T tile[kTrR * kTrPitch];
+  const int k0 = blockIdx.x * kTrK, r0 = blockIdx.y * kTrR, g = blockIdx.z;
+  const T* src = x + (static_cast<long long>(g) * R + r0) * K + k0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int idx = threadIdx.x + j * 256;
+    const int row = idx >> 3, c = idx & 7;
+    const uint4 raw = ptx::ld_nc_v4(src + static_cast<long long>(row) * K + c * 8);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(tile + row * kTrPitch + c * 8);
+    dst[0] = raw.x; dst[1] = raw.y; dst[2] = raw.z; dst[3] = raw.w;
+  }
+  __syncthreads();
+  const int k = threadIdx.x & 63, rb = threadIdx.x >> 6;
+  float f[32];
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    f[i] = to_f32<T>(tile[(rb * 32 + i) * kTrPitch + k]);
+    amax = fmaxf(amax, fabsf(f[i]));
+  }
+  const uint32_t bits = __float_as_uint(amax * (1.0f / 448.0f));
+  int e = static_cast<int>((bits >> 23) & 0xFFu) - 127 + ((bits & 0x7FFFFFu) != 0u ? 1 : 0);
+  e = max(-127, min(126, e));
+  const float inv = __uint_as_float(static_cast<uint32_t>(127 - e) << 23);
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const __nv_fp8x4_e4m3 p4(make_float4(f[4 * i] * inv, f[4 * i + 1] * inv, f[4 * i + 2] * inv, f[4 * i + 3] * inv));
+    w[i] = *reinterpret_cast<const uint32_t*>(&p4);
+  }
+  const int krow = k0 + k;
+  uint8_t* dst = qT + (static_cast<long long>(g) * K + krow) * R + r0 + rb * 32;
+  *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint4*>(dst + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+  const long long atom = (static_cast<long long>(g) * (R / 128) + r0 / 128) * row_tiles + krow / 128;
+  sf[atom * kSfAtomBytes + (krow % 32) * 16 + ((krow % 128) / 32) * 4 + rb] = static_cast<uint8_t>(e + 127);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -348,16 +451,28 @@ cudaError_t mx_launch(const MxGemmProblem& p, cudaStream_t stream, const char** 
   a.tiles_n = p.N / BN;
   a.sfa_row_tiles = (p.M + 127) / 128;
   a.sfb_row_tiles = (p.N + 127) / 128;
-  a.relu = p.relu;
-  a.sf_addr_plain = p.sf_addr_plain;
+  a.bias = static_cast<const __nv_bfloat16*>(p.bias);
+  a.bias_group_stride = p.bias_group_stride;
+  a.aux = static_cast<const __nv_bfloat16*>(p.aux);
+  a.ld_aux = p.ld_aux;
+  a.aux_group_stride = p.aux_group_stride;
+  a.epi = p.epilogue;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
     attr_err = cudaFuncSetAttribute(mx_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return attr_err;
-  const long long tiles = static_cast<long long>(a.tiles_m) * a.tiles_n * p.G;
-  mx_gemm_kernel<BN><<<static_cast<unsigned>(tiles), kMxThreads, C::SMEM_BYTES, stream>>>(ta, tb_, a);
+  a.num_tiles = static_cast<long long>(a.tiles_m) * a.tiles_n * p.G;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  const long long resident = static_cast<long long>(sms) * (BN == 256 ? 1 : 2);
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(a.num_tiles, p.max_ctas > 0 ? p.max_ctas : resident));
+  mx_gemm_kernel<BN><<<grid, kMxThreads, C::SMEM_BYTES, stream>>>(ta, tb_, a);
   return cudaGetLastError();
 }
 
@@ -375,7 +490,10 @@ cudaError_t mx_gemm_launch(const MxGemmProblem& p, cudaStream_t stream, const ch
   int bn = p.block_n;
   if (bn == 0) bn = (p.N % 256 == 0) ? 256 : 128;
   if (bn == 256 && p.N % 256 != 0) return fail("MX GEMM: block_n 256 needs N % 256 == 0");
-  if (static_cast<long long>((p.M + kBM - 1) / kBM) * (p.N / bn) * p.G > 0x7fffffffLL) return fail("MX GEMM: too many tiles");
+  if (p.epilogue == MX_EPI_RELU_BWD && (p.aux == nullptr || (reinterpret_cast<uintptr_t>(p.aux) & 15) || p.ld_aux % 8 || p.aux_group_stride % 8))
+    return fail("MX GEMM: the ReLU-backward epilogue needs a 16-byte aligned aux operand");
+  if (p.bias != nullptr && ((reinterpret_cast<uintptr_t>(p.bias) & 15) || p.bias_group_stride % 8))
+    return fail("MX GEMM: bias must be 16-byte aligned");
   if (bn == 256) return mx_launch<256>(p, stream, why);
   if (bn == 128) return mx_launch<128>(p, stream, why);
   return fail("MX GEMM: block_n must be 128 or 256");
@@ -393,6 +511,21 @@ cudaError_t mx_quantize(const void* x, void* q, void* sf, int groups, int rows, 
   else
     mx_quantize_kernel<__half><<<blocks, 256, 0, stream>>>(static_cast<const __half*>(x), static_cast<uint8_t*>(q),
                                                            static_cast<uint8_t*>(sf), total, rows, k, row_tiles);
+  return cudaGetLastError();
+}
+
+cudaError_t mx_quantize_transpose(const void* x, void* qT, void* sf, int groups, int rows, int k, int elem_type,
+                                  cudaStream_t stream) {
+  if (rows % kTrR != 0 || k % kTrK != 0 || (elem_type != ET_F16 && elem_type != ET_BF16)) return cudaErrorInvalidValue;
+  if (groups == 0 || rows == 0 || k == 0) return cudaSuccess;
+  const dim3 grid(k / kTrK, rows / kTrR, groups);
+  const int row_tiles = (k + 127) / 128;
+  if (elem_type == ET_BF16)
+    mx_quantize_transpose_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(qT),
+                                                                            static_cast<uint8_t*>(sf), rows, k, row_tiles);
+  else
+    mx_quantize_transpose_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(x), static_cast<uint8_t*>(qT),
+                                                                     static_cast<uint8_t*>(sf), rows, k, row_tiles);
   return cudaGetLastError();
 }
 

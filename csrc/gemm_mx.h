@@ -18,6 +18,13 @@ inline long long mx_sf_bytes(int groups, long long rows, long long k) {
 cudaError_t mx_quantize(const void* x, void* q, void* sf, int groups, int rows, int k, int elem_type,
                         cudaStream_t stream);
 
+// x [G, R, K] -> qT e4m3 [G, K, R] quantised along R, sf of an operand with K rows and reduction length R.
+// R % 128 == 0, K % 64 == 0.
+cudaError_t mx_quantize_transpose(const void* x, void* qT, void* sf, int groups, int rows, int k, int elem_type,
+                                  cudaStream_t stream);
+
+enum MxEpilogue : int { MX_EPI_NONE = 0, MX_EPI_RELU = 1, MX_EPI_RELU_BWD = 2 };   // RELU_BWD: D = aux > 0 ? acc : 0
+
 struct MxGemmProblem {
   int M = 0, N = 0, K = 0, G = 1;
   const void* a = nullptr;       // e4m3 [G, M, K]
@@ -26,9 +33,13 @@ struct MxGemmProblem {
   const void* sfb = nullptr;
   void* d = nullptr;             // bf16 [G, M, N]
   long long ldd = 0, d_group_stride = 0;
-  int relu = 0;                  // D = max(acc, 0)
+  const void* bias = nullptr;    // bf16 [G, N]: D = epilogue(acc + bias[n])
+  long long bias_group_stride = 0;
+  const void* aux = nullptr;     // MX_EPI_RELU_BWD: bf16 [G, M, N] forward activation
+  long long ld_aux = 0, aux_group_stride = 0;
+  int epilogue = 0;              // MxEpilogue
   int block_n = 0;               // 128 or 256 (0: 256 when N % 256 == 0)
-  int sf_addr_plain = 0;         // debug switch, see gemm_mx.cu
+  int max_ctas = 0;              // 0: one wave of resident CTAs
 };
 
 cudaError_t mx_gemm_launch(const MxGemmProblem& p, cudaStream_t stream, const char** why = nullptr);

@@ -44,14 +44,92 @@ def test_mx_gemm_is_exact_on_exactly_representable_operands(G, M, N, K, bn):
     assert torch.equal(y.float(), ref.to(torch.bfloat16).float())
 
 
-def test_mx_ffn_close_to_bf16_ffn():
+def test_mx_quantize_transpose_kernel_matches_definition():
+    _need_gpu()
+    from tutel_b200.ops import mx
+    torch.manual_seed(3)
+    w = (torch.randn(2, 256, 192, device='cuda') * torch.exp(torch.randn(2, 1, 192, device='cuda'))).to(torch.bfloat16)
+    q, sf = mx.mx_quantize_transpose(w)                               # [2, 192, 256] quantised along the 256
+    rq, rsf = mx.mx_quantize_reference(w.transpose(1, 2).contiguous())
+    assert q.shape == (2, 192, 256)
+    assert torch.equal(q.view(torch.uint8), rq.view(torch.uint8))
+    assert torch.equal(sf, rsf)
+
+
+@pytest.mark.parametrize('bn', [128, 256])
+def test_mx_gemm_epilogues(bn):
+    _need_gpu()
+    from tutel_b200.ops import mx
+    torch.manual_seed(4)
+    G, M, N, K = 2, 300, 512, 256
+    a = torch.randn(G, M, K, device='cuda', dtype=torch.bfloat16)
+    b = torch.randn(G, N, K, device='cuda', dtype=torch.bfloat16)
+    bias = torch.randn(G, N, device='cuda', dtype=torch.bfloat16)
+    aux = torch.randn(G, M, N, device='cuda', dtype=torch.bfloat16)
+    aux[0, 0, :8] = 0                                                  # zero (and -0) activations pass no gradient
+    aux[0, 1, :8] = -0.0
+    aq, sa = mx.mx_quantize(a)
+    bq, sb = mx.mx_quantize(b)
+    acc = torch.matmul(mx.mx_dequantize(aq, sa), mx.mx_dequantize(bq, sb).transpose(1, 2))
+    plain = mx.mx_gemm(aq, sa, bq, sb, block_n=bn).float()
+    assert float((plain - acc).abs().max() / acc.abs().max()) < 8e-3
+    want = torch.relu(acc + bias.float().unsqueeze(1))
+    got = mx.mx_gemm(aq, sa, bq, sb, bias=bias, epilogue=mx.EPI_RELU, block_n=bn).float()
+    assert float((got - want).abs().max() / want.abs().max()) < 8e-3 and float(got.min()) >= 0
+    got = mx.mx_gemm(aq, sa, bq, sb, aux=aux, epilogue=mx.EPI_RELU_BWD, block_n=bn).float()
+    assert torch.equal(got, torch.where(aux > 0, plain, torch.zeros_like(plain)))
+    # a persistent grid smaller than the tile count walks the same tiles
+    few = mx.mx_gemm(aq, sa, bq, sb, block_n=bn, max_ctas=3).float()
+    assert torch.equal(few, plain)
+
+
+def test_mx_ffn_forward_and_gradients_close_to_fp32():
     _need_gpu()
     from tutel_b200.ops import mx
     torch.manual_seed(2)
     E, C, M, H = 2, 256, 512, 1024
-    x = torch.randn(E, C, M, device='cuda', dtype=torch.bfloat16)
-    w1 = (torch.randn(E, H, M, device='cuda') * M ** -0.5).to(torch.bfloat16)
-    w2 = (torch.randn(E, H, M, device='cuda') * H ** -0.5).to(torch.bfloat16)
-    y = mx.mx_ffn(x, w1, w2).float()
-    ref = torch.matmul(torch.relu(torch.matmul(x.float(), w1.float().transpose(1, 2))), w2.float())
-    assert float((y - ref).norm() / ref.norm()) < 0.06
+    x = torch.randn(E, C, M, device='cuda', dtype=torch.bfloat16, requires_grad=True)
+    w1 = (torch.randn(E, H, M, device='cuda') * M ** -0.5).to(torch.bfloat16).requires_grad_()
+    w2 = (torch.randn(E, H, M, device='cuda') * H ** -0.5).to(torch.bfloat16).requires_grad_()
+    b1 = (torch.randn(E, H, device='cuda') * 0.1).to(torch.bfloat16).requires_grad_()
+    b2 = (torch.randn(E, M, device='cuda') * 0.1).to(torch.bfloat16).requires_grad_()
+    y = mx.fused_relu_ffn_mx(x, w1, b1, w2, b2)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    got = [y] + [t.grad for t in (x, w1, b1, w2, b2)]
+    xf, w1f, b1f, w2f, b2f = (t.detach().float().requires_grad_() for t in (x, w1, b1, w2, b2))
+    ref = torch.matmul(torch.relu(torch.matmul(xf, w1f.transpose(1, 2)) + b1f.unsqueeze(1)), w2f) + b2f.unsqueeze(1)
+    ref.backward(dy.float())
+    want = [ref] + [t.grad for t in (xf, w1f, b1f, w2f, b2f)]
+    # y, dw2, db2 do not pass through the ReLU mask: plain quantisation error.  dx, dw1, db1 do: the mask comes from the
+    # fp8 forward, so a few per cent of the entries near zero flip against the fp32 oracle and each flip costs a whole
+    # entry (measured ~0.16 relative, the same as the row-scaled fp8 path) - the direction must still agree.
+    for name, g, w in zip(('y', 'dx', 'dw1', 'db1', 'dw2', 'db2'), got, want):
+        g = g.detach().float()
+        rel = float((g - w).norm() / w.norm())
+        cos = float((g * w).sum() / (g.norm() * w.norm()))
+        if name in ('y', 'dw2', 'db2'):
+            assert rel < 0.07, (name, rel)
+        else:
+            assert rel < 0.3 and cos > 0.96, (name, rel, cos)
+
+
+def test_moe_layer_with_mx_experts_trains_like_bf16():
+    _need_gpu()
+    from tutel_b200 import moe
+    outs = {}
+    for mode in (None, 'mx'):
+        torch.manual_seed(5)
+        layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2}, model_dim=256,
+                              experts={'type': 'ffn', 'num_experts_per_device': 2, 'hidden_size_per_expert': 512,
+                                       'activation_fn': lambda t: torch.nn.functional.relu(t), **({'fp8': mode} if mode else {})},
+                              seeds=(1, 1, 1)).cuda().to(torch.bfloat16)
+        assert layer.experts.mx == (mode == 'mx')
+        x = torch.randn(4, 128, 256, device='cuda', dtype=torch.bfloat16, requires_grad=True)
+        y = layer(x)
+        (y.float().pow(2).mean() + layer.l_aux).backward()
+        outs[mode] = (y.detach().float(), x.grad.float(), layer.experts.batched_fc1_w.grad.float())
+    for i, (a, b) in enumerate(zip(outs[None], outs['mx'])):
+        rel = float((a - b).norm() / a.norm())
+        cos = float((a * b).sum() / (a.norm() * b.norm()))
+        assert (rel < 0.08) if i == 0 else (rel < 0.3 and cos > 0.96), (i, rel, cos)

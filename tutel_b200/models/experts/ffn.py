@@ -17,6 +17,7 @@ import torch
 import torch.nn.functional as F
 
 from ...ops import gemm as G
+from ...ops import mx as MX
 from ...parallel import communicate as C
 
 
@@ -33,8 +34,14 @@ class FusedExpertsNetwork(torch.nn.Module):
         self.sharded_count = sharded_count
         self.hidden_size = hidden_size_per_expert // sharded_count
         self.output_dim = output_dim or model_dim
-        # fp8=True (or TUTEL_B200_FP8=1): expert GEMMs of the FORWARD pass run in e4m3 with per-row / per-channel scales
-        self.fp8 = bool(int(os.environ.get('TUTEL_B200_FP8', '0'))) if fp8 is None else bool(fp8)
+        # fp8=True / 'row' (or TUTEL_B200_FP8=1): forward and data-gradient expert GEMMs in e4m3 with per-row / per-channel
+        # scales (also inside the fused engine).  fp8='mx' (TUTEL_B200_FP8=mx): OCP MX - e4m3 with one power-of-two scale
+        # per 32 elements, applied by the tensor core (ops/mx.py, csrc/gemm_mx.cu); runs on the unfused path.
+        mode = os.environ.get('TUTEL_B200_FP8', '0') if fp8 is None else fp8
+        mode = str(mode).lower()
+        assert mode in ('0', '1', 'true', 'false', 'none', 'row', 'mx'), 'fp8 must be a bool, "row" or "mx" (got %r)' % (fp8,)
+        self.fp8 = mode in ('1', 'true', 'row')
+        self.mx = mode == 'mx'
 
         if activation_fn_with_self is not None:
             assert activation_fn is None, 'Option `activation_fn_with_self` has been specified, please keep exactly one of them.'
@@ -139,7 +146,9 @@ class FusedExpertsNetwork(torch.nn.Module):
             if not relu:
                 y = self.activation_fn(y)
             return G.skinny_linear(y, w2, b2, 'kn', row_counts)
-        if self._act_kind in G.FWD_EPILOGUE and G.can_use_tcgen05(x, w1) and G.can_use_tcgen05(x, w2):
+        if self.mx and self._act_kind == 'relu' and row_counts is None and MX.can_use_mx(x, w1, w2):
+            y = MX.fused_relu_ffn_mx(x, w1, b1, w2, b2)
+        elif self._act_kind in G.FWD_EPILOGUE and G.can_use_tcgen05(x, w1) and G.can_use_tcgen05(x, w2):
             if self.fp8 and self._act_kind == 'relu' and x.size(-1) % 16 == 0 and w1.size(1) % 16 == 0:
                 y = G.fused_relu_ffn_fp8(x, w1, b1, w2, b2, row_counts)
             else:

@@ -16,7 +16,7 @@ against it, and it documents the number format:
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Any, Optional, Tuple
 
 import torch
 
@@ -94,16 +94,40 @@ def mx_quantize(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return (q[0] if squeeze else q), sf
 
 
-def mx_gemm(a: torch.Tensor, sfa: torch.Tensor, b: torch.Tensor, sfb: torch.Tensor, relu: bool = False,
-            block_n: int = 0, _sf_addr_plain: bool = False) -> torch.Tensor:
-    """``a [G, M, K] @ b [G, N, K]^T`` -> bf16 [G, M, N]; both operands from :func:`mx_quantize`."""
+EPI_NONE, EPI_RELU, EPI_RELU_BWD = 0, 1, 2
+
+
+def mx_quantize_transpose(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """x [G, R, K] -> MX copy of ``x^T`` ([G, K, R], quantised along R) without a 16-bit transpose (one launch)."""
+    G, R, K = x.shape
+    if x.is_cuda and x.element_size() == 2 and backend.has_ext() and R % 128 == 0 and K % 64 == 0:
+        backend.count_launch()
+        q, sf = backend.require_ext().mx_quantize_transpose(x.contiguous())
+        return q, sf
+    return mx_quantize(x.transpose(1, 2).contiguous())
+
+
+def mx_gemm(a: torch.Tensor, sfa: torch.Tensor, b: torch.Tensor, sfb: torch.Tensor, bias: Optional[torch.Tensor] = None,
+            aux: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE, block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
+    """``epilogue(a [G, M, K] @ b [G, N, K]^T + bias [G, N])`` -> bf16 [G, M, N]; operands from :func:`mx_quantize`.
+    ``EPI_RELU``: max(., 0);  ``EPI_RELU_BWD``: keep the result where ``aux`` (the forward activation) is positive."""
     if a.is_cuda and backend.has_ext():
         backend.count_launch()
-        return backend.require_ext().mx_gemm(a, sfa, b, sfb, bool(relu), int(block_n), bool(_sf_addr_plain))
+        if bias is not None:
+            bias = bias.reshape(a.size(0), b.size(1)).to(torch.bfloat16).contiguous()
+        if aux is not None:
+            aux = aux.to(torch.bfloat16).contiguous()
+        return backend.require_ext().mx_gemm(a, sfa, b, sfb, bias, aux, int(epilogue), int(block_n), int(max_ctas))
     if a.is_cuda and not backend.allow_fallback():
         raise RuntimeError('mx_gemm: the native extension is required on a GPU')
     y = torch.matmul(mx_dequantize(a, sfa), mx_dequantize(b, sfb).transpose(1, 2))
-    return (torch.relu(y) if relu else y).to(torch.bfloat16)
+    if bias is not None:
+        y = y + bias.float().reshape(a.size(0), 1, b.size(1))
+    if epilogue == EPI_RELU:
+        y = torch.relu(y)
+    elif epilogue == EPI_RELU_BWD:
+        y = torch.where(aux.float() > 0, y, torch.zeros_like(y))
+    return y.to(torch.bfloat16)
 
 
 _MX_WEIGHT_CACHE = {}
@@ -122,7 +146,7 @@ def mx_weight(w: torch.Tensor, transpose: bool = False):
     if hit is not None and hit[0] == stamp and hit[3]() is anchor:
         return hit[1], hit[2]
     src = w.detach()
-    q, sf = mx_quantize((src.transpose(1, 2) if transpose else src).contiguous())
+    q, sf = mx_quantize_transpose(src.contiguous()) if transpose else mx_quantize(src.contiguous())
     if len(_MX_WEIGHT_CACHE) > 256:
         for k in [k for k, v in _MX_WEIGHT_CACHE.items() if v[3]() is None]:
             del _MX_WEIGHT_CACHE[k]
@@ -130,16 +154,54 @@ def mx_weight(w: torch.Tensor, transpose: bool = False):
     return q, sf
 
 
-def mx_linear(x: torch.Tensor, w: torch.Tensor, w_layout: str = 'nk', relu: bool = False) -> torch.Tensor:
-    """``x [G, R, K] @ W`` with both operands quantised to MX fp8 on the fly (weights cached); W is [G, N, K] ('nk') or
-    [G, K, N] ('kn').  Inference / forward only."""
+def mx_linear(x: torch.Tensor, w: torch.Tensor, w_layout: str = 'nk', bias: Optional[torch.Tensor] = None,
+              epilogue: int = EPI_NONE, aux: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``epilogue(x [G, R, K] @ W + bias)`` with both operands quantised to MX fp8 on the fly (weights cached); W is
+    [G, N, K] ('nk') or [G, K, N] ('kn')."""
     xq, xs = mx_quantize(x)
     wq, ws = mx_weight(w, transpose=(w_layout == 'kn'))
-    return mx_gemm(xq, xs, wq, ws, relu=relu)
+    return mx_gemm(xq, xs, wq, ws, bias=bias, aux=aux, epilogue=epilogue)
+
+
+def can_use_mx(x: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor) -> bool:
+    """bf16 tensors on a GPU, every GEMM dimension a multiple of 128 (K steps and scale atoms are 128 wide)."""
+    return (x.is_cuda and backend.has_ext() and x.dtype == torch.bfloat16 and w1.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
+            and x.dim() == 3 and x.size(-1) % 128 == 0 and w1.size(1) % 128 == 0 and w2.size(2) % 128 == 0)
+
+
+class FusedReluFFNMx(torch.autograd.Function):
+    """ReLU expert FFN ``relu(x @ w1^T + b1) @ w2 + b2`` (x [E, C, M], w1 [E, H, M], w2 [E, H, Mo]: the layout of
+    models/experts/ffn.py) with MX fp8 forward and data-gradient GEMMs - scales applied by the tensor core - and 16-bit
+    weight-gradient GEMMs on the master weights.  Same structure as ``ops.gemm.FusedReluFFNFp8`` (row scales)."""
+
+    @staticmethod
+    def forward(ctx: Any, x, w1, b1, w2, b2):
+        act = mx_linear(x, w1, 'nk', b1, EPI_RELU)
+        y = mx_linear(act, w2, 'kn', b2)
+        ctx.save_for_backward(x, w1, w2, act)
+        ctx.has_b1, ctx.has_b2 = b1 is not None, b2 is not None
+        return y
+
+    @staticmethod
+    def backward(ctx: Any, dy: torch.Tensor):
+        from . import gemm as _gemm
+        x, w1, w2, act = ctx.saved_tensors
+        dy = dy.contiguous()
+        dh = mx_linear(dy, w2, 'nk', None, EPI_RELU_BWD, aux=act)       # dy @ W2^T: W2 [H, Mo] is K-major for it
+        dw2 = _gemm.raw_gemm(act, dy, a_mn=True, b_mn=True) if ctx.needs_input_grad[3] else None
+        db2 = _gemm.column_sums(dy) if ctx.has_b2 and ctx.needs_input_grad[4] else None
+        dx = mx_linear(dh, w1, 'kn') if ctx.needs_input_grad[0] else None   # dh @ W1: W1^T [M, H] K-major
+        dw1 = _gemm.raw_gemm(dh, x, a_mn=True, b_mn=True) if ctx.needs_input_grad[1] else None
+        db1 = _gemm.column_sums(dh) if ctx.has_b1 and ctx.needs_input_grad[2] else None
+        return dx, dw1, db1, dw2, db2
+
+
+def fused_relu_ffn_mx(x, w1, b1, w2, b2):
+    b1 = None if b1 is None else b1.reshape(w1.size(0), -1)
+    b2 = None if b2 is None else b2.reshape(w2.size(0), -1)
+    return FusedReluFFNMx.apply(x, w1, b1, w2, b2)
 
 
 def mx_ffn(x: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor) -> torch.Tensor:
-    """Expert FFN forward ``relu(x @ w1^T) @ w2`` for x [E, C, M], w1 [E, H, M], w2 [E, H, M] (the layout of
-    ``models/experts/ffn.py``) in MX fp8: 2 quantisation launches + 2 GEMMs (ReLU fused into the first)."""
-    h = mx_linear(x, w1, 'nk', relu=True)
-    return mx_linear(h, w2, 'kn')
+    """Bias-free shorthand of :func:`fused_relu_ffn_mx`."""
+    return fused_relu_ffn_mx(x, w1, None, w2, None)

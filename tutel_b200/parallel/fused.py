@@ -415,6 +415,8 @@ def engine_for(layer, x: torch.Tensor, crit, d: int):
     if isinstance(ex, FusedExpertsNetwork):
         if ex._act_kind not in G.FWD_EPILOGUE or ex.skip_expert or (ex.fp8 and ex._act_kind != 'relu'):
             return None
+        if getattr(ex, 'mx', False):
+            return None     # MX block-scaled experts run on the unfused path (ops/mx.py)
         if ex.fp8 and (layer.model_dim % 16 or ex.hidden_size % 16 or ex.output_dim % 16):
             return None
         if ex.batched_fc1_w.dtype != x.dtype or (layer.model_dim % 8) or (ex.hidden_size % 8) or (ex.output_dim % 8):
