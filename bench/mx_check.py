@@ -34,7 +34,7 @@ def crafted(mode, G, M, N, K, dev, seed=0):
     return a.to(dev), ea.to(dev), b.to(dev), eb.to(dev)
 
 
-def run_exact(tag, mode, G, M, N, K, block_n, small_grid):
+def run_exact(tag, mode, G, M, N, K, block_n, small_grid, cg=1):
     import torch
     from tutel_b200.ops import mx
     dev = torch.device('cuda')
@@ -42,11 +42,11 @@ def run_exact(tag, mode, G, M, N, K, block_n, small_grid):
     aq, bq = a.to(torch.float8_e4m3fn), b.to(torch.float8_e4m3fn)
     sa, sb = mx.pack_scales(ea), mx.pack_scales(eb)
     ref = torch.matmul(mx.mx_dequantize(aq, sa), mx.mx_dequantize(bq, sb).transpose(1, 2))
-    y = mx.mx_gemm(aq, sa, bq, sb, block_n=block_n, max_ctas=(5 if small_grid else 0))
+    y = mx.mx_gemm(aq, sa, bq, sb, block_n=block_n, cta_group=cg, max_ctas=((4 if cg == 2 else 5) if small_grid else 0))
     torch.cuda.synchronize()
     want = ref.to(torch.bfloat16).float()
     bad = (y.float() != want)
-    rec = {'case': tag, 'mode': mode, 'shape': [G, M, N, K], 'block_n': block_n, 'max_ctas': 5 if small_grid else 0,
+    rec = {'case': tag, 'mode': mode, 'shape': [G, M, N, K], 'block_n': block_n, 'cta_group': cg, 'small_grid': bool(small_grid),
            'mismatch': int(bad.sum()), 'of': bad.numel(), 'max_abs': float((y.float() - want).abs().max())}
     if rec['mismatch']:
         idx = bad.nonzero()[:6].tolist()
@@ -59,6 +59,20 @@ def run_exact(tag, mode, G, M, N, K, block_n, small_grid):
         rec['bad_cols'] = int(bad.any(-2).sum())
     print(json.dumps(rec), flush=True)
     return rec['mismatch'] == 0
+
+
+def group_exact_cg2(small_grid):
+    """CTA pairs (cta_group::2, 256 x 256 tiles): scales of A per CTA, scales of B in both."""
+    import torch
+    from tutel_b200.ops import backend
+    backend.require_ext().set_spin_timeout(5.0)
+    ok = True
+    cases = [('cg2_ones', 'ones', 1, 256, 256, 128), ('cg2_rows', 'rows', 1, 256, 256, 128), ('cg2_kblk', 'kblocks', 1, 256, 256, 128),
+             ('cg2_rand', 'random', 1, 256, 256, 128), ('cg2_tail', 'random', 1, 100, 256, 256), ('cg2_wrap', 'random', 2, 300, 512, 1024),
+             ('cg2_big', 'random', 2, 1000, 1024, 2048)]
+    for tag, mode, G, M, N, K in cases:
+        ok = run_exact(tag, mode, G, M, N, K, 256, small_grid, cg=2) and ok
+    print(json.dumps({'group': 'exact_cg2', 'small_grid': bool(small_grid), 'ok': ok}), flush=True)
 
 
 def group_exact(small_grid, quick):
@@ -107,7 +121,7 @@ def group_random():
     print(json.dumps({'group': 'random', 'ok': ok}), flush=True)
 
 
-def group_perf():
+def group_perf(cg=1):
     import torch
     from tutel_b200.ops import backend, gemm, mx
     backend.require_ext().set_spin_timeout(20.0)
@@ -135,6 +149,15 @@ def group_perf():
         wq, ws = mx.mx_quantize(w)
         flops = 2.0 * G * M * N * K
         rec = {'shape': [G, M, N, K]}
+        if cg == 2:
+            ms = timeit(lambda: mx.mx_gemm(xq, xs, wq, ws, block_n=256, cta_group=2))
+            rec['mx_cg2_ms'] = round(ms, 4)
+            rec['mx_cg2_tflops'] = round(flops / ms / 1e9, 1)
+            ms = timeit(lambda: mx.mx_gemm(xq, xs, wq, ws, block_n=256, cta_group=1))
+            rec['mx_cg1_ms'] = round(ms, 4)
+            rec['mx_cg1_tflops'] = round(flops / ms / 1e9, 1)
+            print(json.dumps(rec), flush=True)
+            continue
         for bn in (128, 256):
             if N % bn:
                 continue
@@ -161,6 +184,9 @@ def group_perf():
         rec['mx_bias_relu_ms'] = round(ms, 4)
         print(json.dumps(rec), flush=True)
         out.append(rec)
+    if cg == 2:
+        print(json.dumps({'group': 'perf_cg2', 'ok': True}), flush=True)
+        return
     # expert FFN of the flagship layer on one GPU (8 experts x 1024 rows, 4096 -> 14336 -> 4096), forward + backward
     E, C, M, H = 8, 1024, 4096, 14336
     x = torch.randn(E, C, M, device='cuda', dtype=torch.bfloat16, requires_grad=True)
@@ -206,6 +232,7 @@ def main():
     ap.add_argument('--small_grid', type=int, default=0)     # 5 persistent CTAs: every CTA walks several tiles
     ap.add_argument('--quick', type=int, default=0)
     ap.add_argument('--no_perf', action='store_true')
+    ap.add_argument('--only', default='')               # comma-separated group names of the plan
     args = ap.parse_args()
     if args.group == 'exact':
         return group_exact(bool(args.small_grid), bool(args.quick))
@@ -213,12 +240,22 @@ def main():
         return group_random()
     if args.group == 'perf':
         return group_perf()
+    if args.group == 'perf_cg2':
+        return group_perf(2)
+    if args.group == 'exact_cg2':
+        return group_exact_cg2(bool(args.small_grid))
     os.makedirs(args.out, exist_ok=True)
     plan = [('exact_sub', ['--group', 'exact'], 240),
             ('exact_small_grid', ['--group', 'exact', '--small_grid', '1'], 100),
-            ('random', ['--group', 'random'], 150)]
+            ('random', ['--group', 'random'], 150),
+            ('exact_cg2', ['--group', 'exact_cg2'], 120),
+            ('exact_cg2_small_grid', ['--group', 'exact_cg2', '--small_grid', '1'], 120)]
+    if args.only:
+        plan = [p for p in plan if p[0] in args.only.split(',')]
     if not args.no_perf:
-        plan.append(('perf', ['--group', 'perf'], 200))
+        plan.append(('perf_cg2', ['--group', 'perf_cg2'], 200))
+        if not args.only:
+            plan.append(('perf', ['--group', 'perf'], 200))
     summary = {}
     for name, extra, tmo in plan:
         t0 = time.time()

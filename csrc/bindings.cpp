@@ -433,7 +433,7 @@ std::vector<at::Tensor> mx_quantize_transpose(const at::Tensor& x) {
 // epilogue: 0 none, 1 ReLU, 2 ReLU backward (d = aux > 0 ? acc : 0 with aux bf16 [G, M, N])
 at::Tensor mx_gemm(const at::Tensor& a, const at::Tensor& sfa, const at::Tensor& b, const at::Tensor& sfb,
                    const c10::optional<at::Tensor>& bias, const c10::optional<at::Tensor>& aux, int64_t epilogue,
-                   int64_t block_n, int64_t max_ctas) {
+                   int64_t block_n, int64_t cta_group, int64_t max_ctas) {
   TORCH_CHECK(a.is_cuda() && b.is_cuda() && sfa.is_cuda() && sfb.is_cuda() && a.dim() == 3 && b.dim() == 3);
   TORCH_CHECK(a.is_contiguous() && b.is_contiguous() && sfa.is_contiguous() && sfb.is_contiguous());
   TORCH_CHECK(a.scalar_type() == at::kFloat8_e4m3fn && b.scalar_type() == at::kFloat8_e4m3fn &&
@@ -460,6 +460,7 @@ at::Tensor mx_gemm(const at::Tensor& a, const at::Tensor& sfa, const at::Tensor&
   }
   p.epilogue = static_cast<int>(epilogue);
   p.block_n = static_cast<int>(block_n);
+  p.cta_group = static_cast<int>(cta_group);
   p.max_ctas = static_cast<int>(max_ctas);
   const char* why = nullptr;
   cudaError_t e = tb::mx_gemm_launch(p, cur_stream(), &why);

@@ -5,18 +5,22 @@
 // dtype); the row-scaled e4m3 path of gemm_sm100.cu is what the fused engine uses, this kernel is the finer-grained
 // alternative (outliers only cost the 32 elements next to them their precision, not the whole row).
 //
-// Layout of one CTA (192 threads, one 128 x BN output tile, K walked in 128-element = 128-byte steps):
-//   warp 0      TMA producer: A tile [128 x 128 B] and B tile [BN x 128 B] (SWIZZLE_128B) plus the two scale atoms
-//               (512 B per 128 rows, plain bulk copies) per stage, all completing on the stage's "full" mbarrier
+// Layout of one CTA (192 threads; K walked in 128-element = 128-byte steps):
+//   warp 0      TMA producer: A tile [128 x 128 B] and B tile (SWIZZLE_128B) plus the scale atoms (512 B per 128 rows)
+//               per stage, all completing on the stage's "full" mbarrier
 //   warp 1      one elected lane: tcgen05.cp (scales smem -> TMEM; 32 lanes x 4 columns per 128 rows, replicated over
 //               the four lane quarters) followed by four K=32 MMAs whose descriptors select byte 0..3 of those columns;
 //               tcgen05.commit releases the stage.  tcgen05.cp and tcgen05.mma of one thread execute in issue order,
 //               so the scale columns are single-buffered.
 //   warps 2-5   epilogue: tcgen05.ld (thread = accumulator row) -> bias / ReLU in fp32 -> packed bf16 in registers ->
 //               accumulator released -> (ReLU-backward mask) -> 16-byte global stores, overlapping the next tile
-// Persistent (one CTA per SM for BN = 256: 4 stages, 198 KB; two per SM for BN = 128: 3 stages, 100 KB, TMEM 2 x 256
-// columns).  Tensor memory holds ONE accumulator (BN columns) plus 4 + BN / 32 scale columns: a second 256-column
+// Persistent.  Tensor memory holds ONE accumulator (BN columns) plus 4 + BN / 32 scale columns: a second 256-column
 // accumulator would not leave room for the scales, hence the register hand-off instead of double buffering.
+// Variants:  CG = 2 (default for M > 128, N % 256 == 0): a CTA pair owns a 256 x 256 tile, cta_group::2 MMAs; each CTA
+//            stages its 128 A rows, half of the B tile, its A scales and ALL B scales (6 stages, 207 KB);
+//            CG = 1, BN = 256: 4 stages (198 KB), one CTA per SM;  CG = 1, BN = 128: 3 stages (100 KB), two CTAs per SM.
+// Measured on a B200 (bench/mx_check.py, profiles/r2/mx): 2.77-3.10 PFLOP/s (CG = 2) on 8192 x {4096, 14336} x {4096,
+// 14336}, row-scaled fp8 kernel of gemm_sm100.cu 2.58-3.00, bf16 1.60-1.70.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -38,19 +42,21 @@ constexpr int kBK = 128;                 // e4m3 elements = bytes per K step (on
 constexpr int kSfAtomBytes = 512;        // scales of 128 rows x 128 K elements
 constexpr int kMxThreads = 192;
 
-template <int BN>
+template <int CG, int BN>
 struct MxCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 3;
+  static constexpr int BN_CTA = BN / CG;                        // B rows this CTA stages (a pair splits the B tile)
+  static constexpr int STAGES = (CG == 2) ? 6 : ((BN == 256) ? 4 : 3);
   static constexpr uint32_t A_BYTES = kBM * kBK;
-  static constexpr uint32_t B_BYTES = BN * kBK;
+  static constexpr uint32_t B_BYTES = BN_CTA * kBK;
   static constexpr uint32_t OP_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t SFB_BYTES = kSfAtomBytes * (BN / 128);
+  static constexpr uint32_t SFB_BYTES = kSfAtomBytes * (BN / 128);   // scales of ALL BN columns, in every CTA
   static constexpr uint32_t SF_BYTES = kSfAtomBytes + SFB_BYTES;
   static constexpr uint32_t BAR_BYTES = 192;
   static constexpr uint32_t SMEM_BYTES = 1024 + STAGES * (OP_BYTES + SF_BYTES) + BAR_BYTES;
   static constexpr uint32_t SFA_COL = BN;            // TMEM columns: [0, BN) accumulator, then 4 of A scales, then B's
   static constexpr uint32_t SFB_COL = BN + 4;
   static constexpr uint32_t TMEM_COLS = (BN == 256) ? 512 : 256;
+  static constexpr int CTAS_PER_SM = (CG == 1 && BN == 128) ? 2 : 1;
 };
 
 struct MxArgs {
@@ -76,18 +82,33 @@ __device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, u
 }
 
 // 32 rows x 16 bytes of shared memory -> TMEM lanes 0..31 (copied to all four lane quarters), 4 columns.
+// With cta_group::2 the copy runs in both CTAs of the pair, each from its own shared memory into its own TMEM.
+template <int CG>
 __device__ __forceinline__ void tmem_cp_32x128b_warpx4(uint32_t taddr, uint64_t sdesc) {
-  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+  else
+    asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
 }
 
+template <int CG>
 __device__ __forceinline__ void umma_mxf8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t sfa,
                                           uint32_t sfb, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb)
-      : "memory");
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb)
+        : "memory");
+  }
 }
 
 // Output tiles are walked in bands of 8 row tiles so that co-resident CTAs share A and B tiles in L2.
@@ -103,10 +124,14 @@ __device__ __forceinline__ void decode_tile(long long t, int tiles_m, int tiles_
   n_blk = in_band / rows;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kMxThreads, (BN == 256) ? 1 : 2)
-mx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const MxArgs args) {
-  using C = MxCfg<BN>;
+template <int CG, int BN>
+__global__ void __launch_bounds__(kMxThreads, MxCfg<CG, BN>::CTAS_PER_SM)
+mx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmSFA, const __grid_constant__ CUtensorMap tmSFB, const MxArgs args) {
+  using C = MxCfg<CG, BN>;
+  static_assert(CG == 1 || BN == 256, "CTA pairs work on 256 x 256 tiles");
+  const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+  const bool is_leader = (cta_rank == 0);
   extern __shared__ uint8_t smem_raw[];
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -128,6 +153,10 @@ mx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
+    if constexpr (CG == 2) {
+      ptx::prefetch_tensormap(&tmSFA);
+      ptx::prefetch_tensormap(&tmSFB);
+    }
   }
   if (warp == 2 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -135,46 +164,60 @@ mx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_init(empty_bar(s), 1);
     }
     ptx::mbar_init(tfull_bar, 1);
-    ptx::mbar_init(tempty_bar, 4);     // one arrival per epilogue warp
+    ptx::mbar_init(tempty_bar, 4 * CG);     // one arrival per epilogue warp of every CTA of the group
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc<1>(tmem_slot, C::TMEM_COLS);
+  if (warp == 1) ptx::tmem_alloc<CG>(tmem_slot, C::TMEM_COLS);
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
   const int num_kb = args.K / kBK;
 
-  // Persistent: CTA b works on tiles b, b + gridDim.x, ...; the TMA producer runs ahead into the next tile while the
-  // epilogue warps still hold the previous one in registers.
+  // Persistent: CTA (pair) b works on tiles b, b + grid, ...; the TMA producer runs ahead into the next tile while the
+  // epilogue warps still hold the previous one in registers.  A pair (CG == 2) shares one 256 x 256 tile: each CTA
+  // stages its 128 rows of A, HALF of the B tile (the tensor core reads the other half from the peer's shared memory)
+  // and the scales of its A rows and of all B columns; the leader issues every tcgen05 instruction for both.
+  const long long tile_first = blockIdx.x / CG, tile_step = gridDim.x / CG;
+  constexpr int kTileM = kBM * CG;
   if (warp == 0) {
     // =============================== TMA producer ===============================
     int s = 0;
     uint32_t ph = 0;
-    for (long long t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+    for (long long t = tile_first; t < args.num_tiles; t += tile_step) {
       int g, m_blk, n_blk;
       decode_tile(t, args.tiles_m, args.tiles_n, g, m_blk, n_blk);
-      const int m0 = m_blk * kBM, n0 = n_blk * BN;
+      const int m0 = m_blk * kTileM + static_cast<int>(cta_rank) * kBM, n0 = n_blk * BN;
       const uint8_t* sfa_g = args.sfa + static_cast<long long>(g) * num_kb * args.sfa_row_tiles * kSfAtomBytes;
       const uint8_t* sfb_g = args.sfb + static_cast<long long>(g) * num_kb * args.sfb_row_tiles * kSfAtomBytes;
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(empty_bar(s), ph ^ 1u);
         if (ptx::elect_one()) {
           const uint32_t fb = full_bar(s);
-          ptx::mbar_expect_tx(fb, C::OP_BYTES + C::SF_BYTES);
-          ptx::tma_load_3d(smem_a(s), &tmA, fb, kb * kBK, m0, g);
-          ptx::tma_load_3d(smem_b(s), &tmB, fb, kb * kBK, n0, g);
-          bulk_load(smem_sfa(s), sfa_g + (static_cast<long long>(kb) * args.sfa_row_tiles + m_blk) * kSfAtomBytes,
-                    kSfAtomBytes, fb);
-          bulk_load(smem_sfb(s),
-                    sfb_g + (static_cast<long long>(kb) * args.sfb_row_tiles + n_blk * (BN / 128)) * kSfAtomBytes,
-                    C::SFB_BYTES, fb);
+          if constexpr (CG == 1) {
+            ptx::mbar_expect_tx(fb, C::OP_BYTES + C::SF_BYTES);
+            ptx::tma_load_3d(smem_a(s), &tmA, fb, kb * kBK, m0, g);
+            ptx::tma_load_3d(smem_b(s), &tmB, fb, kb * kBK, n0, g);
+            bulk_load(smem_sfa(s), sfa_g + (static_cast<long long>(kb) * args.sfa_row_tiles + m_blk) * kSfAtomBytes,
+                      kSfAtomBytes, fb);
+            bulk_load(smem_sfb(s),
+                      sfb_g + (static_cast<long long>(kb) * args.sfb_row_tiles + n_blk * (BN / 128)) * kSfAtomBytes,
+                      C::SFB_BYTES, fb);
+          } else {
+            // everything is credited to the LEADER's barrier; the scale atoms travel as [128 x uint32] rows of a tensor
+            // map (a plain bulk copy could only signal a barrier of the destination CTA)
+            if (is_leader) ptx::mbar_expect_tx(fb, 2 * (C::OP_BYTES + C::SF_BYTES));
+            ptx::tma_load_3d_2sm(smem_a(s), &tmA, fb, kb * kBK, m0, g);
+            ptx::tma_load_3d_2sm(smem_b(s), &tmB, fb, kb * kBK, n0 + static_cast<int>(cta_rank) * C::BN_CTA, g);
+            ptx::tma_load_3d_2sm(smem_sfa(s), &tmSFA, fb, 0, m_blk * CG + static_cast<int>(cta_rank), g * num_kb + kb);
+            ptx::tma_load_3d_2sm(smem_sfb(s), &tmSFB, fb, 0, n_blk * (BN / 128), g * num_kb + kb);
+          }
         }
         __syncwarp();
         if (++s == C::STAGES) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && (CG == 1 || is_leader)) {
     // =============================== MMA issuer ===============================
     int s = 0;
     uint32_t ph = 0, tph = 0;
@@ -186,11 +229,11 @@ mx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // scale format UE8M0 at [23], M >> 4 at [24,29); the scale byte of a K=32 step goes to [4,6) (B) and [29,31) (A).
     // (The same byte index is mirrored into bits [30,32) of the scale addresses, as CUTLASS does; measured: the
     // hardware takes it from the descriptor, results are identical without the mirror.)
-    constexpr uint32_t idesc0 = (static_cast<uint32_t>(BN >> 3) << 17) | (1u << 23) | (static_cast<uint32_t>(kBM >> 4) << 24);
+    constexpr uint32_t idesc0 = (static_cast<uint32_t>(BN >> 3) << 17) | (1u << 23) | (static_cast<uint32_t>((kBM * CG) >> 4) << 24);
     const uint32_t d_tmem = tmem_base;
     const uint32_t sfa_tmem = tmem_base + C::SFA_COL;
     const uint32_t sfb_tmem = tmem_base + C::SFB_COL;
-    for (long long t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+    for (long long t = tile_first; t < args.num_tiles; t += tile_step) {
       ptx::mbar_wait(tempty_bar, tph ^ 1u);     // the epilogue warps have read the previous tile out of TMEM
       ptx::tc_fence_after();
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -199,10 +242,10 @@ mx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (ptx::elect_one()) {
           const uint32_t a_lo = ((smem_a(s) >> 4) & 0x3FFFu) | (1u << 16);
           const uint32_t b_lo = ((smem_b(s) >> 4) & 0x3FFFu) | (1u << 16);
-          tmem_cp_32x128b_warpx4(sfa_tmem, (static_cast<uint64_t>(sf_hi) << 32) | ((smem_sfa(s) >> 4) & 0x3FFFu) | (1u << 16));
+          tmem_cp_32x128b_warpx4<CG>(sfa_tmem, (static_cast<uint64_t>(sf_hi) << 32) | ((smem_sfa(s) >> 4) & 0x3FFFu) | (1u << 16));
 #pragma unroll
           for (int j = 0; j < BN / 128; ++j)
-            tmem_cp_32x128b_warpx4(sfb_tmem + 4u * j, (static_cast<uint64_t>(sf_hi) << 32) |
+            tmem_cp_32x128b_warpx4<CG>(sfb_tmem + 4u * j, (static_cast<uint64_t>(sf_hi) << 32) |
                                                           (((smem_sfb(s) + j * kSfAtomBytes) >> 4) & 0x3FFFu) | (1u << 16));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -210,17 +253,17 @@ mx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t bd = (static_cast<uint64_t>(op_hi) << 32) | (b_lo + 2u * k);
             const uint32_t idesc = idesc0 | (static_cast<uint32_t>(k) << 4) | (static_cast<uint32_t>(k) << 29);
             const uint32_t sub = static_cast<uint32_t>(k) << 30;
-            umma_mxf8(d_tmem, ad, bd, idesc, sfa_tmem + sub, sfb_tmem + sub, (kb | k) != 0);
+            umma_mxf8<CG>(d_tmem, ad, bd, idesc, sfa_tmem + sub, sfb_tmem + sub, (kb | k) != 0);
           }
-          ptx::umma_commit<1>(empty_bar(s));
-          if (kb == num_kb - 1) ptx::umma_commit<1>(tfull_bar);
+          ptx::umma_commit<CG>(empty_bar(s));
+          if (kb == num_kb - 1) ptx::umma_commit<CG>(tfull_bar);
         }
         __syncwarp();
         if (++s == C::STAGES) { s = 0; ph ^= 1u; }
       }
       tph ^= 1u;
     }
-  } else {
+  } else if (warp >= 2) {
     // =============================== epilogue ===============================
     // Phase A moves the whole accumulator row of this thread into registers as packed bf16 (bias / ReLU applied in
     // fp32 on the way) and hands TMEM back to the MMA warp; phase B (ReLU-backward mask, global stores) then overlaps
@@ -229,11 +272,11 @@ mx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     uint32_t tph = 0;
     const int epi = args.epi;
-    for (long long t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+    for (long long t = tile_first; t < args.num_tiles; t += tile_step) {
       int g, m_blk, n_blk;
       decode_tile(t, args.tiles_m, args.tiles_n, g, m_blk, n_blk);
       const int n0 = n_blk * BN;
-      const int row = m_blk * kBM + q * 32 + lane;
+      const int row = m_blk * kTileM + static_cast<int>(cta_rank) * kBM + q * 32 + lane;
       const __nv_bfloat16* bias = args.bias == nullptr ? nullptr : args.bias + static_cast<long long>(g) * args.bias_group_stride + n0;
       uint32_t pk[BN / 2];
       ptx::mbar_wait(tfull_bar, tph);
@@ -264,7 +307,10 @@ mx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar);
+      if (lane == 0) {
+        if constexpr (CG == 1) ptx::mbar_arrive(tempty_bar);
+        else ptx::mbar_arrive_cluster(tempty_bar, 0);
+      }
       tph ^= 1u;
       if (row < args.M) {
         __nv_bfloat16* drow = args.d + static_cast<long long>(g) * args.d_group_stride + static_cast<long long>(row) * args.ldd + n0;
@@ -290,8 +336,8 @@ mx_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<1>(tmem_base, C::TMEM_COLS);
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -432,11 +478,24 @@ bool mx_operand_map(CUtensorMap* map, const void* base, long long rows, long lon
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN>
+// scale atoms [groups * num_kb, row_tiles, 128 x uint32]: one box = `atoms` consecutive 512-byte atoms of one K step
+bool mx_scale_map(CUtensorMap* map, const void* base, long long row_tiles, long long kb_total, int atoms) {
+  EncodeTiledFn enc = mx_encode_fn();
+  if (enc == nullptr) return false;
+  cuuint64_t dims[3] = {128, static_cast<cuuint64_t>(row_tiles), static_cast<cuuint64_t>(kb_total)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(kSfAtomBytes), static_cast<cuuint64_t>(row_tiles) * kSfAtomBytes};
+  cuuint32_t box[3] = {128, static_cast<cuuint32_t>(atoms), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int CG, int BN>
 cudaError_t mx_launch(const MxGemmProblem& p, cudaStream_t stream, const char** why) {
-  using C = MxCfg<BN>;
-  CUtensorMap ta, tb_;
-  if (!mx_operand_map(&ta, p.a, p.M, p.K, p.G, kBM) || !mx_operand_map(&tb_, p.b, p.N, p.K, p.G, BN)) {
+  using C = MxCfg<CG, BN>;
+  CUtensorMap ta, tb_, tsa, tsb;
+  if (!mx_operand_map(&ta, p.a, p.M, p.K, p.G, kBM) || !mx_operand_map(&tb_, p.b, p.N, p.K, p.G, C::BN_CTA)) {
     if (why) *why = "cuTensorMapEncodeTiled failed for an MX operand";
     return cudaErrorInvalidValue;
   }
@@ -447,7 +506,7 @@ cudaError_t mx_launch(const MxGemmProblem& p, cudaStream_t stream, const char** 
   a.ldd = p.ldd;
   a.d_group_stride = p.d_group_stride;
   a.M = p.M; a.N = p.N; a.K = p.K; a.G = p.G;
-  a.tiles_m = (p.M + kBM - 1) / kBM;
+  a.tiles_m = (p.M + kBM * CG - 1) / (kBM * CG);
   a.tiles_n = p.N / BN;
   a.sfa_row_tiles = (p.M + 127) / 128;
   a.sfb_row_tiles = (p.N + 127) / 128;
@@ -457,10 +516,21 @@ cudaError_t mx_launch(const MxGemmProblem& p, cudaStream_t stream, const char** 
   a.ld_aux = p.ld_aux;
   a.aux_group_stride = p.aux_group_stride;
   a.epi = p.epilogue;
+  if (CG == 2) {
+    const long long kb_total = static_cast<long long>(p.G) * (p.K / kBK);
+    if (!mx_scale_map(&tsa, p.sfa, a.sfa_row_tiles, kb_total, 1) || !mx_scale_map(&tsb, p.sfb, a.sfb_row_tiles, kb_total, BN / 128)) {
+      if (why) *why = "cuTensorMapEncodeTiled failed for the MX scales";
+      return cudaErrorInvalidValue;
+    }
+  } else {
+    tsa = ta;
+    tsb = ta;
+  }
+  auto* kern = mx_gemm_kernel<CG, BN>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(mx_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  std::call_once(once, [kern] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return attr_err;
   a.num_tiles = static_cast<long long>(a.tiles_m) * a.tiles_n * p.G;
@@ -470,10 +540,21 @@ cudaError_t mx_launch(const MxGemmProblem& p, cudaStream_t stream, const char** 
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
-  const long long resident = static_cast<long long>(sms) * (BN == 256 ? 1 : 2);
-  const unsigned grid = static_cast<unsigned>(std::min<long long>(a.num_tiles, p.max_ctas > 0 ? p.max_ctas : resident));
-  mx_gemm_kernel<BN><<<grid, kMxThreads, C::SMEM_BYTES, stream>>>(ta, tb_, a);
-  return cudaGetLastError();
+  long long groups = static_cast<long long>(sms) * C::CTAS_PER_SM / CG;    // resident CTAs (pairs)
+  if (p.max_ctas > 0) groups = std::max<long long>(1, std::min<long long>(groups, p.max_ctas / CG));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(std::min<long long>(a.num_tiles, groups) * CG));
+  cfg.blockDim = dim3(kMxThreads);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb_, tsa, tsb, a);
 }
 
 }  // namespace
@@ -494,8 +575,12 @@ cudaError_t mx_gemm_launch(const MxGemmProblem& p, cudaStream_t stream, const ch
     return fail("MX GEMM: the ReLU-backward epilogue needs a 16-byte aligned aux operand");
   if (p.bias != nullptr && ((reinterpret_cast<uintptr_t>(p.bias) & 15) || p.bias_group_stride % 8))
     return fail("MX GEMM: bias must be 16-byte aligned");
-  if (bn == 256) return mx_launch<256>(p, stream, why);
-  if (bn == 128) return mx_launch<128>(p, stream, why);
+  int cg = p.cta_group;
+  if (cg == 0) cg = (bn == 256 && p.M > 128) ? 2 : 1;     // pairs halve the B traffic per SM: 2.8-3.1 vs 2.4-2.6 PFLOP/s
+  if (cg == 2 && bn != 256) return fail("MX GEMM: CTA pairs need block_n 256");
+  if (cg == 2) return mx_launch<2, 256>(p, stream, why);
+  if (bn == 256) return mx_launch<1, 256>(p, stream, why);
+  if (bn == 128) return mx_launch<1, 128>(p, stream, why);
   return fail("MX GEMM: block_n must be 128 or 256");
 }
 

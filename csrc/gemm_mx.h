@@ -39,6 +39,7 @@ struct MxGemmProblem {
   long long ld_aux = 0, aux_group_stride = 0;
   int epilogue = 0;              // MxEpilogue
   int block_n = 0;               // 128 or 256 (0: 256 when N % 256 == 0)
+  int cta_group = 0;             // 1, or 2 = CTA pairs on 256 x 256 tiles (block_n 256 only); 0: auto
   int max_ctas = 0;              // 0: one wave of resident CTAs
 };
 

@@ -108,7 +108,8 @@ def mx_quantize_transpose(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def mx_gemm(a: torch.Tensor, sfa: torch.Tensor, b: torch.Tensor, sfb: torch.Tensor, bias: Optional[torch.Tensor] = None,
-            aux: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE, block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
+            aux: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE, block_n: int = 0, cta_group: int = 0,
+            max_ctas: int = 0) -> torch.Tensor:
     """``epilogue(a [G, M, K] @ b [G, N, K]^T + bias [G, N])`` -> bf16 [G, M, N]; operands from :func:`mx_quantize`.
     ``EPI_RELU``: max(., 0);  ``EPI_RELU_BWD``: keep the result where ``aux`` (the forward activation) is positive."""
     if a.is_cuda and backend.has_ext():
@@ -117,7 +118,7 @@ def mx_gemm(a: torch.Tensor, sfa: torch.Tensor, b: torch.Tensor, sfb: torch.Tens
             bias = bias.reshape(a.size(0), b.size(1)).to(torch.bfloat16).contiguous()
         if aux is not None:
             aux = aux.to(torch.bfloat16).contiguous()
-        return backend.require_ext().mx_gemm(a, sfa, b, sfb, bias, aux, int(epilogue), int(block_n), int(max_ctas))
+        return backend.require_ext().mx_gemm(a, sfa, b, sfb, bias, aux, int(epilogue), int(block_n), int(cta_group), int(max_ctas))
     if a.is_cuda and not backend.allow_fallback():
         raise RuntimeError('mx_gemm: the native extension is required on a GPU')
     y = torch.matmul(mx_dequantize(a, sfa), mx_dequantize(b, sfb).transpose(1, 2))
