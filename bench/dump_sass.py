@@ -35,6 +35,8 @@ LISTINGS = {
     'p2p_stride_copy.sass.txt': r'p2p_stride_copy_kernel',
     'quantize_rows_bf16.sass.txt': r'quantize_rows_kernel<__nv_bfloat16>',
     'skinny_ffn_f32.sass.txt': r'skinny_ffn_kernel<float>',
+    'gemm_mx_2cta_bn256.sass.txt': r'mx_gemm_kernel<2, 256>',
+    'mx_quantize_bf16.sass.txt': r'mx_quantize_kernel<__nv_bfloat16>',
 }
 
 

@@ -149,21 +149,15 @@ def group_perf(cg=1):
         wq, ws = mx.mx_quantize(w)
         flops = 2.0 * G * M * N * K
         rec = {'shape': [G, M, N, K]}
-        if cg == 2:
-            ms = timeit(lambda: mx.mx_gemm(xq, xs, wq, ws, block_n=256, cta_group=2))
-            rec['mx_cg2_ms'] = round(ms, 4)
-            rec['mx_cg2_tflops'] = round(flops / ms / 1e9, 1)
-            ms = timeit(lambda: mx.mx_gemm(xq, xs, wq, ws, block_n=256, cta_group=1))
-            rec['mx_cg1_ms'] = round(ms, 4)
-            rec['mx_cg1_tflops'] = round(flops / ms / 1e9, 1)
-            print(json.dumps(rec), flush=True)
-            continue
-        for bn in (128, 256):
+        for tag, bn, g2 in (('mx_cg2', 256, 2), ('mx_cg1_bn256', 256, 1), ('mx_cg1_bn128', 128, 1)):
             if N % bn:
                 continue
-            ms = timeit(lambda: mx.mx_gemm(xq, xs, wq, ws, block_n=bn))
-            rec['mx_bn%d_ms' % bn] = round(ms, 4)
-            rec['mx_bn%d_tflops' % bn] = round(flops / ms / 1e9, 1)
+            ms = timeit(lambda: mx.mx_gemm(xq, xs, wq, ws, block_n=bn, cta_group=g2))
+            rec[tag + '_ms'] = round(ms, 4)
+            rec[tag + '_tflops'] = round(flops / ms / 1e9, 1)
+        if cg == 2:
+            print(json.dumps(rec), flush=True)
+            continue
         rq, rscale = gemm.quantize_rows(x)
         wq8, wscale = gemm.quantize_rows(w)
         d = torch.empty(G, M, N, device='cuda', dtype=torch.bfloat16)
