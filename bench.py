@@ -38,6 +38,7 @@ def parse():
     ap.add_argument('--no_e2e', action='store_true')
     ap.add_argument('--expert_type', type=str, default='ffn')     # llama_ffn: Mixtral-style SwiGLU block (BASELINE config #3)
     ap.add_argument('--fp8', action='store_true')                  # ours only: e4m3 forward + data-gradient GEMMs
+    ap.add_argument('--graph', default='auto', choices=['auto', 'off'])     # ours, 1 GPU: replay the whole step as one CUDA graph
     ap.add_argument('--fp8_mode', default='row', choices=['row', 'mx'])   # row scales (fused engine) or MX 32-element block scales
     return ap.parse_args()
 
@@ -141,12 +142,36 @@ def main():
             sampler = timers.ClockSampler(device.index or 0).start()  # started early: nvidia-smi needs a moment to spin up
         except Exception:  # noqa
             sampler = None
+    eager_step = step
     first_loss = float(step(x_dev, y_dev).item())          # loss of the very first step (same seeds in both arms)
     warm_done = 1
     for _ in range(max(args.warmup, 3) - 1):
         step(x_dev, y_dev)
         warm_done += 1
     sync()
+    # ours, one GPU: nothing in a step touches the host, so the whole step (zero_grad, forward, loss, backward, SGD) is
+    # recorded once with the framework's public `GraphedTrainStep` and replayed as ONE graph launch per step - the same
+    # kernels do the same work, only the ~40 launches per step are issued by the GPU front end instead of Python.
+    # (Multi-GPU steps number their peer-to-peer transactions on the host and are not captured; the reference's step
+    # reads the capacity back to the host in every forward and cannot be captured at all.)
+    graph_info = {'cuda_graph': False}
+    if args.impl == 'ours' and world == 1 and args.graph == 'auto':
+        try:
+            from tutel_b200.utils.graph import GraphedTrainStep
+            gstep = GraphedTrainStep(eager_step, x_dev, y_dev, warmup=2)
+            warm_done += 3
+            probe = float(gstep(x_dev, y_dev).item())
+            assert probe == probe, 'graph replay produced a NaN loss'
+            warm_done += 1
+
+            def step(x, y):                       # noqa: F811 - same signature, replays the captured step
+                return gstep(x, y)
+            x_dev, y_dev = gstep.static_inputs    # resident inputs of the device-timed loop: no copy in front of a replay
+            graph_info = {'cuda_graph': True, 'launches_per_graph_replay': gstep.launches_per_replay}
+        except Exception as ex:  # noqa - capture not possible on this build: measure the eager step
+            step = eager_step
+            graph_info = {'cuda_graph': False, 'graph_capture_error': repr(ex)[:200]}
+            torch.cuda.synchronize()
     # Keep warming (untimed) until the step time has converged: blocks of 4 steps, stop when two consecutive blocks agree
     # within 2 % on every rank (clocks, the power-cap controller and the allocator settle within a few dozen steps).
     prev_blk, warm_trace = None, []
@@ -251,7 +276,7 @@ def main():
                    'step': 'zero_grad + fwd + nll_loss + bwd (incl. input gradient) + gate-grad all-reduce + SGD',
                    'l2': 'working set (weights %.1f GB + activations) exceeds the 126 MB L2; no explicit flush' % (
                        local_experts * 2 * args.model_dim * args.hidden * 2 / 1e9),
-                   'a2a_ffn_overlap_degree': args.overlap},
+                   'a2a_ffn_overlap_degree': args.overlap, **graph_info},
         'tflops_per_gpu': flops / (ms / args.steps * 1e-3) * 1e-12,
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'loss': float(loss.item()), 'first_step_loss': first_loss,
     }

@@ -211,3 +211,46 @@ def test_quantize_transpose_matches_row_quantisation_of_the_transpose(C):
     q, s = C.quantize_rows(w.transpose(1, 2).contiguous())
     assert qT.shape == (3, 192, 256) and torch.allclose(sT, s, rtol=1e-6)
     assert torch.equal(qT.view(torch.uint8), q.view(torch.uint8))
+
+
+def test_graphed_train_step_matches_eager_training():
+    """zero_grad + forward + loss + backward + SGD of an MoE layer replayed as ONE CUDA graph: same loss trajectory as the
+    eager loop (nothing in a single-GPU step touches the host)."""
+    from tutel_b200 import moe
+    from tutel_b200.utils.graph import GraphedTrainStep
+
+    def build():
+        torch.manual_seed(7)
+        layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2}, model_dim=256,
+                              experts={'type': 'ffn', 'num_experts_per_device': 4, 'hidden_size_per_expert': 512,
+                                       'activation_fn': lambda t: F.relu(t)}, seeds=(1, 1, 1)).cuda().to(torch.bfloat16)
+        opt = torch.optim.SGD(layer.parameters(), lr=1e-2)
+
+        def step(x, y):
+            opt.zero_grad()
+            x.grad = None
+            out = layer(x)
+            loss = F.mse_loss(out.float(), y) + layer.l_aux.float() * 0.01
+            loss.backward()
+            opt.step()
+            return loss
+        return step
+
+    torch.manual_seed(11)
+    xs = [torch.randn(2, 256, 256, device='cuda', dtype=torch.bfloat16) for _ in range(6)]
+    ys = [torch.randn(2, 256, 256, device='cuda') for _ in range(6)]
+    # Both twins first train eagerly on the default stream (the usual situation: a loop that is already running gets
+    # captured).  The constructor then runs `warmup` real steps on the example inputs (the capture itself executes
+    # nothing), so the eager twin takes the same step; from then on both see the same batches.
+    eager, step = build(), build()
+    for fn in (eager, step):
+        for _ in range(2):
+            fn(xs[0].clone().requires_grad_(True), ys[0])
+    eager(xs[0].clone().requires_grad_(True), ys[0])
+    want = [float(eager(x.clone().requires_grad_(True), y)) for x, y in zip(xs[1:], ys[1:])]
+    fast = GraphedTrainStep(step, xs[0].clone().requires_grad_(True), ys[0], warmup=1)
+    got = [float(fast(x, y)) for x, y in zip(xs[1:], ys[1:])]
+    assert fast.launches_per_replay > 5
+    for g, w in zip(got, want):
+        assert abs(g - w) <= 1e-2 * abs(w), (got, want)
+    assert fast.static_inputs[0].grad is not None and float(fast.static_inputs[0].grad.abs().sum()) > 0

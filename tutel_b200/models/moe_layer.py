@@ -304,6 +304,10 @@ class MOELayer(torch.nn.Module):
             out.l_aux = None
             return self.result_func(out) if self.result_func is not None else out
 
+        # Let go of the previous call's auxiliary loss BEFORE building a new autograd graph: it is the one tensor of a step
+        # that outlives it, and through it the gate weight's gradient accumulator - which remembers the stream it was
+        # created on and would otherwise tie a step captured into a CUDA graph (utils/graph.py) to the eager warm-up stream.
+        self.l_aux = None
         original_shape, original_dtype = input.shape, input.dtype
         assert len(original_shape) >= 2, 'Input data must be at least 2D tensor: (s)amples, .., (m)odel_dim'
         reserve_shape = original_shape[-reserve_dims:]
