@@ -58,3 +58,41 @@ def test_mx_gemm_cpu_definition_matches_float_matmul():
     assert float((y - ref).abs().max() / ref.abs().max()) < 0.06
     with pytest.raises(ValueError):
         mx.mx_quantize(torch.randn(1, 4, 96))
+
+
+def test_expert_fp8_modes_select_row_or_mx_paths(monkeypatch):
+    """fp8=True / 'row' -> row-scaled e4m3 (eligible for the fused engine); fp8='mx' -> MX block scales (unfused path)."""
+    from tutel_b200.models.experts.ffn import FusedExpertsNetwork
+    kw = dict(model_dim=128, hidden_size_per_expert=256, num_experts_per_device=2, sharded_count=1)
+    for arg, want in ((None, (False, False)), (False, (False, False)), (True, (True, False)), ('row', (True, False)), ('mx', (False, True))):
+        ex = FusedExpertsNetwork(fp8=arg, **kw)
+        assert (ex.fp8, ex.mx) == want, arg
+    monkeypatch.setenv('TUTEL_B200_FP8', 'mx')
+    ex = FusedExpertsNetwork(**kw)
+    assert ex.mx and not ex.fp8
+    monkeypatch.setenv('TUTEL_B200_FP8', '1')
+    ex = FusedExpertsNetwork(**kw)
+    assert ex.fp8 and not ex.mx
+    with pytest.raises(AssertionError):
+        FusedExpertsNetwork(fp8='int4', **kw)
+    # on CPU the MX path is never taken: the layer computes in the model dtype
+    x = torch.randn(2, 8, 128)
+    assert not mx.can_use_mx(x, ex.batched_fc1_w, ex.batched_fc2_w)
+
+
+def test_mx_epilogues_of_the_cpu_definition():
+    torch.manual_seed(5)
+    a, b = torch.randn(1, 16, 128), torch.randn(1, 128, 128)
+    bias, aux = torch.randn(1, 128), torch.randn(1, 16, 128)
+    aq, sa = mx.mx_quantize(a)
+    bq, sb = mx.mx_quantize(b)
+    acc = torch.matmul(mx.mx_dequantize(aq, sa), mx.mx_dequantize(bq, sb).transpose(1, 2))
+    relu = mx.mx_gemm(aq, sa, bq, sb, bias=bias, epilogue=mx.EPI_RELU).float()
+    assert torch.allclose(relu, torch.relu(acc + bias.unsqueeze(1)).bfloat16().float())
+    bwd = mx.mx_gemm(aq, sa, bq, sb, aux=aux, epilogue=mx.EPI_RELU_BWD).float()
+    assert torch.equal(bwd, torch.where(aux > 0, acc, torch.zeros_like(acc)).bfloat16().float())
+    # the transposing quantiser is the plain one applied to the transpose
+    w = torch.randn(2, 128, 256)
+    q, sf = mx.mx_quantize_transpose(w)
+    rq, rsf = mx.mx_quantize_reference(w.transpose(1, 2).contiguous())
+    assert torch.equal(q.view(torch.uint8), rq.view(torch.uint8)) and torch.equal(sf, rsf)

@@ -99,7 +99,7 @@ def run_layer(env, fused, dtype, nle, steps=3, overlap=1, model_dim=256, hidden=
     if output_dim is not None:
         experts['output_dim'] = output_dim
     if fp8:
-        experts['fp8'] = True
+        experts['fp8'] = fp8          # True / 'row': row scales (fused engine); 'mx': MX block scales (unfused path)
     layer = moe.moe_layer(gate_type={'type': 'top', 'k': 2, 'capacity_factor': 1.5}, model_dim=model_dim, experts=experts,
                           seeds=(1, 1 if same_experts else r + 1, 1), a2a_ffn_overlap_degree=overlap, is_postscore=is_postscore,
                           parallel_type=parallel_type).to(dev).to(dtype)
@@ -224,6 +224,13 @@ def test_fp8(env):
         drift = max(abs(u - v) / max(1e-6, abs(v)) for u, v in zip(a[0], c[0]))
         print('[rank %d] fp8 vs bf16 losses (%s): %s vs %s (max rel. diff %.4f)' % (env.global_rank, expert, a[0], c[0], drift), flush=True)
         check('fp8 loss curve within 5%% of bf16 (%s)' % expert, drift < 5e-2)
+    # MX block-scaled experts (fp8='mx'): the fused engine declines them, the generic exchange feeds the MX GEMMs
+    m = run_layer(env, True, torch.bfloat16, 2, model_dim=256, hidden=512, fp8='mx', steps=6)
+    c = run_layer(env, True, torch.bfloat16, 2, model_dim=256, hidden=512, fp8=False, steps=6)
+    drift = max(abs(u - v) / max(1e-6, abs(v)) for u, v in zip(m[0], c[0]))
+    print('[rank %d] mx vs bf16 losses: %s vs %s (max rel. diff %.4f)' % (env.global_rank, m[0], c[0], drift), flush=True)
+    check('mx loss curve within 5% of bf16', drift < 5e-2)
+    check('mx output close to bf16', ((m[2] - c[2]).norm() / c[2].norm()).item() < 0.1)
 
 
 def test_deep_stack(env):
