@@ -88,6 +88,11 @@ class GraphedTrainStep:
             self._loss = step_fn(*self._inputs)
         self.launches_per_replay = backend.launch_count() - before     # native kernels recorded in the graph
         self._count = backend.count_launch
+        # optimizer-step hooks do not run during a replay: tell the fp8 / MX weight caches (ops/gemm.py, ops/mx.py) that the
+        # weights moved, so that an eager forward after replays re-quantises them (the replays themselves re-quantise
+        # inside the graph and never consult the cache)
+        from ..ops import gemm as _gemm
+        self._weights_moved = _gemm.invalidate_fp8_cache
 
     def __call__(self, *inputs: torch.Tensor):
         with torch.no_grad():
@@ -96,6 +101,7 @@ class GraphedTrainStep:
                     dst.copy_(src, non_blocking=True)
         self._graph.replay()
         self._count(self.launches_per_replay)
+        self._weights_moved()
         return self._loss
 
     @property
